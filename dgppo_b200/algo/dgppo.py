@@ -1,0 +1,354 @@
+"""DGPPO on the B200 kernels: act / step / collect / det rollout / Vh / GAE /
+CBF advantage - the rollout side of the reference's class chain
+DGPPO <- InforMARLLagr <- InforMARL <- Algorithm
+(dgppo/algo/dgppo.py:25-321, informarl.py:28-472).
+
+Constructor arguments, `config`, `params`, `act`, `step`, `collect`,
+`get_Vh`, `update`, `save`, `load` keep the reference's names and meaning.
+Parameters are held as reference-shaped pytrees (NumPy leaves) and as packed
+fp32 device buffers (algo/params.py).  `update` runs the hot-path pre-pass of
+`DGPPO.update` / `update_inner` (deterministic rollout, Vl scan, Vh over all
+(b, T), Dec-OCP GAE, CBF-residual advantage: dgppo.py:136-273) on the GPU and
+returns its products; the PPO minibatch gradient step (dgppo.py:276-321,
+informarl.py:357-457) is the caller's autodiff code and outside this path
+(component 3).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pickle
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..env.base import MultiAgentEnv, ptr, require_cuda, stream_ptr
+from ..trainer.data import Rollout
+from ..trainer.rollout import RNN_DIM, run_rollout
+from ..utils.graph import GraphsTuple
+from . import params as P
+from .base import Algorithm
+
+
+def piecewise_constant_schedule(init_value: float, boundaries_and_scales: Dict[int, float]):
+    """optax.piecewise_constant_schedule (dgppo.py:74-80)."""
+    items = sorted(boundaries_and_scales.items())
+
+    def fn(step: int) -> float:
+        v = init_value
+        for bnd, sc in items:
+            if step >= bnd:
+                v *= sc
+        return v
+    return fn
+
+
+class DGPPO(Algorithm):
+
+    def __init__(self, env: MultiAgentEnv, node_dim: int, edge_dim: int, state_dim: int, action_dim: int,
+                 n_agents: int, actor_gnn_layers: int = 2, Vl_gnn_layers: int = 2, Vh_gnn_layers: int = 1,
+                 gamma: float = 0.99, lr_actor: float = 3e-4, lr_Vl: float = 1e-3, lr_Vh: float = 1e-3,
+                 batch_size: int = 8192, epoch_ppo: int = 1, clip_eps: float = 0.25, gae_lambda: float = 0.95,
+                 coef_ent: float = 1e-2, max_grad_norm: float = 2.0, seed: int = 0, use_rnn: bool = True,
+                 rnn_layers: int = 1, rnn_step: int = 16, use_lstm: bool = False, alpha: float = 10.0,
+                 cbf_eps: float = 1e-2, cbf_weight: float = 1.0, train_steps: int = 1e5,
+                 cbf_schedule: bool = True, **kwargs):
+        super().__init__(env=env, node_dim=node_dim, edge_dim=edge_dim, action_dim=action_dim, n_agents=n_agents)
+        if not use_rnn or use_lstm or rnn_layers != 1:
+            raise NotImplementedError("the B200 kernels cover the default recurrent policy: GRU, 1 layer "
+                                      "(--no-rnn / --use-lstm / --rnn-layers>1 are outside this path)")
+        self.cost_weight = kwargs.get("cost_weight", 0.)
+        self.actor_gnn_layers, self.Vl_gnn_layers, self.Vh_gnn_layers = actor_gnn_layers, Vl_gnn_layers, Vh_gnn_layers
+        self.gamma, self.lr_actor, self.lr_Vl, self.lr_Vh = gamma, lr_actor, lr_Vl, lr_Vh
+        self.batch_size, self.epoch_ppo, self.clip_eps, self.gae_lambda = batch_size, epoch_ppo, clip_eps, gae_lambda
+        self.coef_ent, self.max_grad_norm, self.seed = coef_ent, max_grad_norm, seed
+        self.use_rnn, self.rnn_layers, self.rnn_step, self.use_lstm = use_rnn, rnn_layers, rnn_step, use_lstm
+        self.cost_schedule = kwargs.get("cost_schedule", False)
+        self.state_dim = state_dim
+        self.alpha, self.cbf_eps, self.cbf_weight, self.cbf_schedule = alpha, cbf_eps, cbf_weight, cbf_schedule
+        if self.cbf_schedule:
+            self.cbf_schedule_fn = piecewise_constant_schedule(
+                cbf_weight, {int(train_steps * 0.5): 2, int(train_steps * 0.75): 2})
+
+        self.device = require_cuda()
+        # rnn carry: (rnn_layers, n_agents, n_carries, 64), zeros (GRUCell.initialize_carry; informarl.py:114-124)
+        self.init_rnn_state = torch.zeros((rnn_layers, n_agents, 1, RNN_DIM), device=self.device)
+        self.init_Vl_rnn_state = torch.zeros((rnn_layers, 1, 1, RNN_DIM), device=self.device)
+
+        self.policy_cfg = P.net_cfg(_lib.NET_POLICY, node_dim, edge_dim, actor_gnn_layers, action_dim)
+        self.Vl_cfg = P.net_cfg(_lib.NET_VL, node_dim, edge_dim, Vl_gnn_layers, 1)
+        self.Vh_cfg = P.net_cfg(_lib.NET_VH, node_dim, edge_dim, Vh_gnn_layers, env.n_cost)
+        self._trees = {
+            "policy": P.init_policy_params(node_dim, edge_dim, action_dim, actor_gnn_layers, seed=seed),
+            "Vl": P.init_value_params(node_dim, edge_dim, 1, Vl_gnn_layers, seed=seed + 1),
+            "Vh": P.init_value_params(node_dim, edge_dim, env.n_cost, Vh_gnn_layers, seed=seed + 2),
+        }
+        self._cfgs = {"policy": self.policy_cfg, "Vl": self.Vl_cfg, "Vh": self.Vh_cfg}
+        self._packed: Dict[Tuple[str, int], torch.Tensor] = {}
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(seed)
+        self._np_rng = np.random.default_rng(seed)
+        self.last_prepass: Optional[dict] = None
+
+    # ------------------------------------------------------------ config / params
+    @property
+    def config(self) -> dict:
+        return {
+            'cost_weight': self.cost_weight, 'actor_gnn_layers': self.actor_gnn_layers,
+            'Vl_gnn_layers': self.Vl_gnn_layers, 'gamma': self.gamma, 'lr_actor': self.lr_actor,
+            'lr_Vl': self.lr_Vl, 'batch_size': self.batch_size, 'epoch_ppo': self.epoch_ppo,
+            'clip_eps': self.clip_eps, 'gae_lambda': self.gae_lambda, 'coef_ent': self.coef_ent,
+            'max_grad_norm': self.max_grad_norm, 'seed': self.seed, 'use_rnn': self.use_rnn,
+            'rnn_layers': self.rnn_layers, 'rnn_step': self.rnn_step, 'use_lstm': self.use_lstm,
+            'cost_schedule': self.cost_schedule, 'lr_Vh': self.lr_Vh, 'Vh_gnn_layers': self.Vh_gnn_layers,
+            'alpha': self.alpha, 'cbf_eps': self.cbf_eps, 'cbf_weight': self.cbf_weight,
+            'cbf_schedule': self.cbf_schedule,
+        }
+
+    @property
+    def params(self) -> dict:
+        return {"policy": self._trees["policy"], "Vl": self._trees["Vl"], "Vh": self._trees["Vh"]}
+
+    def set_params(self, name: str, tree: dict) -> None:
+        self._trees[name] = tree
+
+    def packed(self, name: str, params: Optional[dict] = None) -> torch.Tensor:
+        """Device buffer of net `name` for the given params pytree (cached per pytree object)."""
+        tree = (self.params if params is None else params)[name]
+        key = (name, id(tree))
+        buf = self._packed.get(key)
+        if buf is None:
+            if len(self._packed) > 16:
+                self._packed.clear()
+            buf = torch.from_numpy(P.pack_params(tree, self._cfgs[name])).to(self.device)
+            self._packed[key] = buf
+        return buf
+
+    # ------------------------------------------------------------------ helpers
+    def _eps_from_key(self, key, shape) -> torch.Tensor:
+        g = torch.Generator(device=self.device)
+        k = np.asarray(key.detach().cpu() if isinstance(key, torch.Tensor) else key).astype(np.uint64).ravel()
+        g.manual_seed(int(np.bitwise_xor.reduce(k * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1)) % (2 ** 63)))
+        return torch.randn(shape, generator=g, device=self.device, dtype=torch.float32)
+
+    def _policy_call(self, graph: GraphsTuple, rnn_state: torch.Tensor, eps, params):
+        n = self.n_agents
+        single = graph.is_single
+        g = graph.map_arrays(lambda t: t.unsqueeze(0)) if single else graph
+        b = g.nodes.shape[0]
+        rnn_in = rnn_state.reshape(b, n, RNN_DIM).contiguous().float()
+        rnn_out = torch.empty_like(rnn_in)
+        action = torch.empty((b, n, self.action_dim), dtype=torch.float32, device=rnn_in.device)
+        log_pi = torch.empty((b, n), dtype=torch.float32, device=rnn_in.device) if eps is not None else None
+        if eps is not None:
+            eps = eps.reshape(b, n, self.action_dim).contiguous()
+        cfg = self._env.env_cfg()
+        nodes, edges = g.nodes.contiguous(), g.edges.contiguous()
+        recv, send = g.receivers.contiguous(), g.senders.contiguous()
+        _lib.check(_lib.lib().dgppo_gnn_policy(
+            stream_ptr(), C.byref(cfg), C.byref(self.policy_cfg), ptr(self.packed("policy", params)),
+            ptr(nodes), ptr(edges), ptr(recv), ptr(send), 1, ptr(rnn_in), ptr(rnn_out), 1,
+            ptr(eps), 1, ptr(action), ptr(log_pi), 1, b), "dgppo_gnn_policy")
+        new_rnn = rnn_out.reshape(rnn_state.shape)
+        if single:
+            return action[0], (None if log_pi is None else log_pi[0]), new_rnn
+        return action, log_pi, new_rnn
+
+    # ---------------------------------------------------------------- act / step
+    def act(self, graph: GraphsTuple, rnn_state: torch.Tensor, params: Optional[dict] = None):
+        """InforMARL.act (informarl.py:230-239): deterministic mode tanh(mean)."""
+        action, _, rnn_state = self._policy_call(graph, rnn_state, None, params)
+        return action, rnn_state
+
+    def step(self, graph: GraphsTuple, rnn_state: torch.Tensor, key, params: Optional[dict] = None):
+        """InforMARL.step (informarl.py:241-252): sample tanh(mean + std eps), log_pi.
+        `key` seeds the N(0,1) draw (or pass a ready-made tensor of draws)."""
+        shape = graph.nodes.shape[:-2] + (self.n_agents, self.action_dim)
+        eps = key if (isinstance(key, torch.Tensor) and key.dtype == torch.float32 and tuple(key.shape) == tuple(shape)) \
+            else self._eps_from_key(key, shape)
+        action, log_pi, rnn_state = self._policy_call(graph, rnn_state, eps, params)
+        assert action.shape[-2:] == (self.n_agents, self.action_dim)
+        return action, log_pi, rnn_state
+
+    # ------------------------------------------------------------------ rollouts
+    def collect(self, params: dict, b_key, eps: Optional[torch.Tensor] = None, graph0: Optional[GraphsTuple] = None,
+                record=None) -> Rollout:
+        """InforMARL.collect (informarl.py:254-256): jit(vmap(rollout)) over the
+        env keys == one batched rollout.  `b_key`: one key per environment."""
+        if graph0 is None:
+            graph0 = self._env.reset(b_key)
+        b, T = graph0.nodes.shape[0], self._env.max_episode_steps
+        if eps is None:
+            eps = self._eps_from_key(b_key, (b, T, self.n_agents, self.action_dim))
+        return run_rollout(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
+                           self.init_rnn_state, record=record)
+
+    def det_rollout_fn(self, params: dict, b_key, graph0: Optional[GraphsTuple] = None, record=None) -> Rollout:
+        """DGPPO.det_rollout_fn (dgppo.py:108-117): test_rollout with algo.act."""
+        if graph0 is None:
+            graph0 = self._env.reset(b_key)
+        return run_rollout(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
+                           self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True)
+
+    @staticmethod
+    def _record_arrays(rollout: Rollout):
+        """(b, T+1, ...) graph arrays behind a Rollout: the shared record when the
+        Rollout came from run_rollout (graph / next_graph are views of it), else a
+        concatenation of graph and next_graph[:, -1]."""
+        g, ng = rollout.graph, rollout.next_graph
+        T = rollout.rewards.shape[1]
+        out = []
+        for name in ("nodes", "edges", "receivers", "senders"):
+            a, an = getattr(g, name), getattr(ng, name)
+            base = a._base
+            if base is not None and base.shape[1] == T + 1 and base.shape[2:] == a.shape[2:] and \
+                    a.data_ptr() == base.data_ptr() and base.is_contiguous():
+                out.append(base)
+            else:
+                out.append(torch.cat([a, an[:, -1:]], dim=1).contiguous())
+        return out
+
+    # -------------------------------------------------------------------- values
+    def _value_record(self, which: str, rollout: Rollout, params) -> torch.Tensor:
+        """Vh over all (b, T) graphs + the final one (dgppo.py:219-228): the
+        graphs of `rollout.graph` and `rollout.next_graph[:, -1]` are slots
+        0..T of one record; the carry fed to the GRU is `rollout.rnn_states`
+        for t < T and the policy's post-step carry for the final graph."""
+        g = rollout.graph
+        b, T = rollout.rewards.shape
+        n = self.n_agents
+        nodes, edges, recv, send = self._record_arrays(rollout)
+        # carries: t < T as stored; final: act(next_graph[-1], rnn_states[-1]) -> its new carry
+        rnn_rec = torch.empty((b, T + 1, n, RNN_DIM), dtype=torch.float32, device=nodes.device)
+        rnn_rec[:, :T] = rollout.rnn_states.reshape(b, T, n, RNN_DIM)
+        last = GraphsTuple(*[t[:, -1] if isinstance(t, torch.Tensor) else None for t in rollout.next_graph])
+        _, _, final_carry = self._policy_call(last, rollout.rnn_states[:, -1].reshape(b, n, RNN_DIM), None, params)
+        rnn_rec[:, T] = final_carry
+        nc = self._env.n_cost
+        Vh = torch.empty((b, T + 1, n, nc), dtype=torch.float32, device=nodes.device)
+        cfg = self._env.env_cfg()
+        _lib.check(_lib.lib().dgppo_gnn_value(
+            stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
+            ptr(nodes), ptr(edges), ptr(recv), ptr(send), T + 1, ptr(rnn_rec), None, T + 1,
+            ptr(Vh), T + 1, T + 1, b), "dgppo_gnn_value")
+        return Vh
+
+    def get_Vh(self, graph: GraphsTuple, rnn_state: torch.Tensor, params: Optional[dict] = None) -> torch.Tensor:
+        """DGPPO.get_Vh (dgppo.py:128-134)."""
+        n = self.n_agents
+        single = graph.is_single
+        g = graph.map_arrays(lambda t: t.unsqueeze(0)) if single else graph
+        b = g.nodes.shape[0]
+        rnn_in = rnn_state.reshape(b, n, RNN_DIM).contiguous().float()
+        Vh = torch.empty((b, n, self._env.n_cost), dtype=torch.float32, device=rnn_in.device)
+        cfg = self._env.env_cfg()
+        _lib.check(_lib.lib().dgppo_gnn_value(
+            stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
+            ptr(g.nodes.contiguous()), ptr(g.edges.contiguous()), ptr(g.receivers.contiguous()),
+            ptr(g.senders.contiguous()), 1, ptr(rnn_in), None, 1, ptr(Vh), 1, 1, b), "dgppo_gnn_value")
+        return Vh[0] if single else Vh
+
+    def scan_Vl(self, rollout: Rollout, params: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """InforMARL.scan_Vl + final Vl (informarl.py:281-293, dgppo.py:204-216):
+        the centralised value is recurrent over T, so T+1 launches, each over
+        the b graphs of one slot.  -> Vl (b, T+1), carries (b, T+1, 64)."""
+        g = rollout.graph
+        b, T = rollout.rewards.shape
+        nodes, edges, recv, send = self._record_arrays(rollout)
+        d = self._env.graph_dims()
+        dev = nodes.device
+        carry = torch.zeros((b, T + 2, RNN_DIM), dtype=torch.float32, device=dev)
+        carry[:, 0] = self.init_Vl_rnn_state.reshape(RNN_DIM)
+        Vl = torch.empty((b, T + 1), dtype=torch.float32, device=dev)
+        cfg, lib, pv = self._env.env_cfg(), _lib.lib(), self.packed("Vl", params)
+        es = 4
+        for t in range(T + 1):
+            _lib.check(lib.dgppo_gnn_value(
+                stream_ptr(), C.byref(cfg), C.byref(self.Vl_cfg), ptr(pv),
+                nodes.data_ptr() + t * d.n_nodes * d.node_dim * es, edges.data_ptr() + t * d.n_edges * 4 * es,
+                recv.data_ptr() + t * d.n_edges * 4, send.data_ptr() + t * d.n_edges * 4, T + 1,
+                carry.data_ptr() + t * RNN_DIM * es, carry.data_ptr() + (t + 1) * RNN_DIM * es, T + 2,
+                Vl.data_ptr() + t * es, T + 1, 1, b), "dgppo_gnn_value(Vl)")
+        return Vl, carry[:, :T + 1]
+
+    def gae(self, costs, neg_rewards, Vh, Vl) -> Tuple[torch.Tensor, torch.Tensor]:
+        """vmap(compute_dec_ocp_gae) (dgppo.py:232-237; algo/utils.py:11-79)."""
+        b, T, n, nh = costs.shape
+        Qh = torch.empty_like(costs)
+        Ql = torch.empty((b, T), dtype=torch.float32, device=costs.device)
+        _lib.check(_lib.lib().dgppo_gae(stream_ptr(), ptr(costs.contiguous()), ptr(neg_rewards.contiguous()),
+                                         ptr(Vh.contiguous()), ptr(Vl.contiguous()), self.gamma, self.gae_lambda,
+                                         ptr(Qh), ptr(Ql), b, T, n, nh), "dgppo_gae")
+        return Qh, Ql
+
+    def cbf_advantage(self, Ql, Vl, Vh, step: int):
+        """Advantage merge (dgppo.py:239-259) -> A (b,T,n), cbf_deriv, Acbf, is_safe."""
+        b, Tp1, n, nh = Vh.shape
+        T = Tp1 - 1
+        dev = Vh.device
+        A = torch.empty((b, T, n), dtype=torch.float32, device=dev)
+        deriv = torch.empty((b, T, n, nh), dtype=torch.float32, device=dev)
+        acbf = torch.empty_like(deriv)
+        safe = torch.empty((b, T, n), dtype=torch.uint8, device=dev)
+        w = self.cbf_schedule_fn(step) if self.cbf_schedule else self.cbf_weight
+        _lib.check(_lib.lib().dgppo_cbf_advantage(
+            stream_ptr(), ptr(Ql.contiguous()), ptr(Vl.contiguous()), ptr(Vh.contiguous()),
+            float(self._env.dt), float(self.alpha), float(self.cbf_eps), float(w),
+            ptr(A), ptr(deriv), ptr(acbf), ptr(safe), b, T, n, nh), "dgppo_cbf_advantage")
+        return A, deriv, acbf, safe.bool()
+
+    # -------------------------------------------------------------------- update
+    def update(self, rollout: Rollout, step: int) -> dict:
+        """Hot-path pre-pass of DGPPO.update / update_inner (dgppo.py:136-273).
+
+        Runs the deterministic rollout, Vl, Vh (stochastic and deterministic
+        records), both GAE passes and the CBF advantage merge on the GPU.  The
+        tensors the PPO minibatch scan consumes (dgppo.py:276-289) are left in
+        `self.last_prepass`; the gradient step itself is outside this path."""
+        b = rollout.dones.shape[0]
+        assert rollout.dones.shape[0] * rollout.dones.shape[1] >= self.batch_size
+        key = self._np_rng.integers(0, 2 ** 31 - 1, size=b)
+        det_rollout = self.det_rollout_fn(self.params, key)
+        Vl, Vl_carries = self.scan_Vl(rollout)
+        Vh = self._value_record("Vh", rollout, None)
+        Qh, Ql = self.gae(rollout.costs, -rollout.rewards, Vh, Vl)
+        A, deriv, acbf, is_safe = self.cbf_advantage(Ql, Vl, Vh, step)
+        Vh_det = self._value_record("Vh", det_rollout, None)
+        Qh_det, _ = self.gae(det_rollout.costs, -det_rollout.rewards, Vh_det, Vl)
+        # host-side batching indices exactly as dgppo.py:155-159
+        idx = np.arange(b)
+        self._np_rng.shuffle(idx)
+        T = rollout.dones.shape[1]
+        rnn_chunk_ids = np.array(np.array_split(np.arange(T), T // self.rnn_step))
+        batch_idx = np.array(np.array_split(idx, idx.shape[0] // (self.batch_size // T)))
+        self.last_prepass = dict(det_rollout=det_rollout, bTp1_Vl=Vl, bT_Vl_rnn_states=Vl_carries[:, :T],
+                                 bTp1ah_Vh=Vh, bTah_Qh=Qh, bT_Ql=Ql, bTa_A=A, bTah_cbf_deriv=deriv,
+                                 bTah_Acbf=acbf, bTa_is_safe=is_safe, bTp1ah_Vh_det=Vh_det,
+                                 bTah_Qh_det=Qh_det, batch_idx=batch_idx, rnn_chunk_ids=rnn_chunk_ids)
+        return {"eval/safe_data": float(is_safe.float().mean())}
+
+    # ---------------------------------------------------------------- save / load
+    def save(self, save_dir: str, step: int):
+        """Pickle the parameter pytrees (informarl_lagr.py:311-317)."""
+        model_dir = os.path.join(save_dir, str(step))
+        os.makedirs(model_dir, exist_ok=True)
+        for name, fn in (("policy", "actor.pkl"), ("Vl", "Vl.pkl"), ("Vh", "Vh.pkl")):
+            with open(os.path.join(model_dir, fn), "wb") as f:
+                pickle.dump(self._trees[name], f)
+
+    def load(self, load_dir: str, step: int):
+        """Load pickled parameter pytrees (informarl_lagr.py:319-327)."""
+        path = os.path.join(load_dir, str(step))
+        for name, fn in (("policy", "actor.pkl"), ("Vl", "Vl.pkl"), ("Vh", "Vh.pkl")):
+            with open(os.path.join(path, fn), "rb") as f:
+                tree = pickle.load(f)
+            self._trees[name] = _to_numpy_tree(tree)
+        self._packed.clear()
+
+
+def _to_numpy_tree(t):
+    if isinstance(t, dict):
+        return {k: _to_numpy_tree(v) for k, v in t.items()}
+    return np.asarray(t, np.float32)

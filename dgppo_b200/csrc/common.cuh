@@ -1,0 +1,68 @@
+// Shared device helpers for libdgppo_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "dgppo_abi.h"
+
+namespace dgppo {
+
+// --- individually rounded fp32 arithmetic --------------------------------
+// Every value that feeds a mask comparison, an index, or an env state is
+// computed with these: nvcc may not contract them into FFMA, and div/sqrt are
+// IEEE-rounded regardless of -prec-div / fast-math flags.  This is the same
+// arithmetic NumPy performs in oracle/env_np.py, which makes the env kernels
+// comparable bit for bit.
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+// jnp.linalg.norm of a 2-vector: sqrt(dx*dx + dy*dy)
+__device__ __forceinline__ float norm2(float dx, float dy) {
+  return fsqrt(fadd(fmul(dx, dx), fmul(dy, dy)));
+}
+// jnp.clip(x, lo, hi) = min(max(x, lo), hi) for finite x
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  return fminf(fmaxf(x, lo), hi);
+}
+// NaN-propagating min (XLA / NumPy reduce-min semantics)
+__device__ __forceinline__ float nanmin(float a, float b) {
+  return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b);
+}
+
+struct GraphDims {
+  int sd, nd, n_on, N, E, n_ag, n_ao, n, g;
+};
+
+__host__ __device__ inline bool is_lidar(int kind) { return kind != DGPPO_ENV_MPE_SPREAD; }
+__host__ __device__ inline bool is_bicycle(int kind) { return kind == DGPPO_ENV_LIDAR_BICYCLE_TARGET; }
+
+__host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
+  GraphDims d;
+  d.n = c.n_agents;
+  d.g = c.n_agents;
+  d.sd = is_bicycle(c.kind) ? 5 : 4;
+  d.nd = d.sd + 3;
+  const bool lid = is_lidar(c.kind);
+  d.n_on = (c.n_obs > 0) ? (lid ? c.top_k * c.n_agents : c.n_obs) : 0;
+  d.N = d.n + d.g + d.n_on + 1;
+  d.n_ag = (c.kind == DGPPO_ENV_LIDAR_SPREAD || c.kind == DGPPO_ENV_MPE_SPREAD) ? d.g : 1;
+  d.n_ao = (c.n_obs > 0) ? (lid ? c.top_k : c.n_obs) : 0;
+  d.E = d.n * d.n + d.n * d.n_ag + d.n * d.n_ao;
+  return d;
+}
+
+inline int check_env_cfg(const DgppoEnvCfg* c) {
+  if (!c) return DGPPO_EINVAL;
+  if (c->kind < 0 || c->kind > 3) return DGPPO_ENOTSUP;
+  if (c->n_agents < 1 || c->n_obs < 0) return DGPPO_EINVAL;
+  if (is_lidar(c->kind) && c->n_obs > 0) {
+    if (c->n_rays < 1 || c->n_rays > 1024) return DGPPO_ENOTSUP;
+    if (c->top_k < 1 || c->top_k > c->n_rays) return DGPPO_EINVAL;
+  }
+  return 0;
+}
+
+}  // namespace dgppo

@@ -1,0 +1,421 @@
+// K1 (dynamics + reward + cost), K2 (LiDAR), K3 (radius graph) for sm_100a.
+//
+// All three are HBM-/latency-bound integer-and-fp32 kernels: one warp (K1,
+// K2) or one CTA (K3) per environment, per-env tiles staged in shared memory,
+// coalesced float4 / int stores for the graph record.  Arithmetic follows the
+// reference op by op with individually rounded fp32 operations (common.cuh),
+// so masks, indices and states match oracle/env_np.py bit for bit.
+#include "common.cuh"
+
+namespace dgppo {
+
+struct EnvConsts {
+  int kind, n, n_obs, n_rays, top_k;
+  float dt, R, R_diag, R_obs, car2, car, car_obs, d2g;
+  float lo[5], hi[5];
+};
+
+static EnvConsts make_consts(const DgppoEnvCfg& c) {
+  EnvConsts k;
+  k.kind = c.kind; k.n = c.n_agents; k.n_obs = c.n_obs; k.n_rays = c.n_rays; k.top_k = c.top_k;
+  k.dt = (float)c.dt;
+  k.R = (float)c.comm_radius;
+  k.R_diag = (float)(c.comm_radius + 1.0);          // lidar_spread.py:64
+  k.R_obs = (float)(c.comm_radius - 1e-1);          // lidar_spread.py:87
+  k.car2 = (float)(c.car_radius * 2.0);             // lidar_env/base.py:188
+  k.car = (float)c.car_radius;                      // lidar_env/base.py:197
+  k.car_obs = (float)(c.car_radius + c.obs_radius); // mpe/base.py:181
+  k.d2g = (float)c.dist2goal;
+  const float A = (float)c.area_size;
+  if (is_bicycle(c.kind)) {                         // lidar_bicycle_target.py:120-123
+    const float lo[5] = {0.f, 0.f, -1.f, -1.f, -0.5f}, hi[5] = {A, A, 1.f, 1.f, 0.5f};
+    for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
+  } else {
+    const float v = (c.kind == DGPPO_ENV_MPE_SPREAD) ? 1.0f : 0.5f;   // mpe/base.py:243-246 | lidar_env/base.py:273-276
+    const float lo[5] = {0.f, 0.f, -v, -v, 0.f}, hi[5] = {A, A, v, v, 0.f};
+    for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
+  }
+  return k;
+}
+
+// ------------------------------------------------------------------- K1
+// One warp per environment; lanes stride over agents / goals.
+constexpr int K1_WARPS = 4;
+
+__global__ void __launch_bounds__(K1_WARPS * 32)
+env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ goal,
+                const float* __restrict__ obs_nodes, const float* __restrict__ action,
+                float* __restrict__ next_agent, float* __restrict__ reward,
+                float* __restrict__ cost, int io_pitch, int b) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * K1_WARPS + warp;
+  if (env >= b) return;
+  const int n = k.n, sd = is_bicycle(k.kind) ? 5 : 4;
+  float* px = smem + warp * (5 * n);
+  float* py = px + n;
+  float* an2 = py + n;     // |clipped action|^2
+  float* d2g = an2 + n;    // per-goal distance
+  float* far = d2g + n;
+
+  const float* ag = agent + (size_t)env * n * sd;
+  const float* ac = action + (size_t)env * io_pitch * n * 2;
+  float* nx = next_agent + (size_t)env * n * sd;
+
+  for (int i = lane; i < n; i += 32) {
+    float s[5];
+    for (int c = 0; c < sd; ++c) s[c] = ag[i * sd + c];
+    const float a0 = clampf(ac[i * 2 + 0], -1.f, 1.f);      // clip_action, env/base.py:84-86
+    const float a1 = clampf(ac[i * 2 + 1], -1.f, 1.f);
+    px[i] = s[0]; py[i] = s[1];
+    const float nrm = norm2(a0, a1);
+    an2[i] = fmul(nrm, nrm);
+    float o[5];
+    if (sd == 5) {                                           // lidar_bicycle_target.py:96-106
+      const float theta = atan2f(s[3], s[2]);
+      const float theta_next = fadd(theta, fmul(fmul(fmul(s[4], a0), k.dt), 10.f));
+      o[0] = fadd(s[0], fmul(fmul(s[4], cosf(theta)), k.dt));
+      o[1] = fadd(s[1], fmul(fmul(s[4], sinf(theta)), k.dt));
+      o[2] = cosf(theta_next);
+      o[3] = sinf(theta_next);
+      o[4] = fadd(s[4], fmul(fmul(a1, k.dt), 10.f));
+    } else {                                                 // lidar_env/base.py:146-147
+      o[0] = fadd(fmul(s[2], k.dt), s[0]);
+      o[1] = fadd(fmul(s[3], k.dt), s[1]);
+      o[2] = fadd(fmul(fmul(a0, 10.f), k.dt), s[2]);
+      o[3] = fadd(fmul(fmul(a1, 10.f), k.dt), s[3]);
+    }
+    for (int c = 0; c < sd; ++c) nx[i * sd + c] = clampf(o[c], k.lo[c], k.hi[c]);
+  }
+  __syncwarp();
+
+  // cost on the pre-step state (lidar_env/base.py:180-207, mpe/base.py:164-191)
+  const bool lid = is_lidar(k.kind);
+  for (int i = lane; i < n; i += 32) {
+    const float xi = px[i], yi = py[i];
+    float mind = INFINITY;
+    for (int j = 0; j < n; ++j) {
+      float d = norm2(fsub(xi, px[j]), fsub(yi, py[j]));
+      d = fadd(d, (i == j) ? 1e6f : 0.f);
+      mind = fminf(mind, d);
+    }
+    float c0 = fsub(k.car2, mind);
+    float c1 = 0.f;
+    if (k.n_obs > 0) {
+      float mo = INFINITY;
+      if (lid) {
+        const float* h = obs_nodes + ((size_t)env * n + i) * k.top_k * 2;
+        for (int q = 0; q < k.top_k; ++q)
+          mo = nanmin(mo, norm2(fsub(h[2 * q], xi), fsub(h[2 * q + 1], yi)));
+        c1 = fsub(k.car, mo);
+      } else {
+        const float* ob = obs_nodes + (size_t)env * k.n_obs * 4;
+        for (int q = 0; q < k.n_obs; ++q)
+          mo = fminf(mo, norm2(fsub(xi, ob[4 * q]), fsub(yi, ob[4 * q + 1])));
+        c1 = fsub(k.car_obs, mo);
+      }
+    }
+    c0 = (c0 <= 0.f) ? fsub(c0, 0.5f) : fadd(c0, 0.5f);
+    c1 = (c1 <= 0.f) ? fsub(c1, 0.5f) : fadd(c1, 0.5f);
+    if (lid) { c0 = clampf(c0, -1.f, 1.f); c1 = (c1 != c1) ? c1 : clampf(c1, -1.f, 1.f); }
+    else     { c0 = fmaxf(c0, -1.f);       c1 = fmaxf(c1, -1.f); }
+    cost[((size_t)env * io_pitch * n + i) * 2 + 0] = c0;
+    cost[((size_t)env * io_pitch * n + i) * 2 + 1] = c1;
+  }
+
+  // reward (lidar_spread.py:35-52, lidar_target.py:35-52)
+  const float* gl = goal + (size_t)env * n * sd;
+  const bool spread = (k.kind == DGPPO_ENV_LIDAR_SPREAD || k.kind == DGPPO_ENV_MPE_SPREAD);
+  for (int q = lane; q < n; q += 32) {
+    const float gx = gl[q * sd], gy = gl[q * sd + 1];
+    float d;
+    if (spread) {
+      d = INFINITY;
+      for (int j = 0; j < n; ++j) d = fminf(d, norm2(fsub(gx, px[j]), fsub(gy, py[j])));
+    } else {
+      d = norm2(fsub(gx, px[q]), fsub(gy, py[q]));
+    }
+    d2g[q] = d;
+    far[q] = (d > k.d2g) ? 1.f : 0.f;
+  }
+  __syncwarp();
+  if (lane == 0) {                       // left-to-right means (oracle seq_mean)
+    float s0 = d2g[0], s1 = far[0], s2 = an2[0];
+    for (int j = 1; j < n; ++j) { s0 = fadd(s0, d2g[j]); s1 = fadd(s1, far[j]); s2 = fadd(s2, an2[j]); }
+    const float fn = (float)n;
+    float r = 0.f;
+    r = fsub(r, fmul(fdiv(s0, fn), 0.01f));
+    r = fsub(r, fmul(fdiv(s1, fn), 0.001f));
+    r = fsub(r, fmul(fdiv(s2, fn), 0.0001f));
+    reward[(size_t)env * io_pitch] = r;
+  }
+}
+
+// ------------------------------------------------------------------- K2
+// One warp per (environment, agent); lanes stride over rays.  Obstacle
+// records are read with warp-uniform 128-bit loads (served by L1 after the
+// first agent of the env touches them); the per-ray alpha, the stable rank
+// (counting sort over the warp's rays) and the hit points stay on chip.
+constexpr int K2_WARPS = 4;
+
+__device__ __forceinline__ bool key_less(float aj, int j, float ar, int r) {
+  // stable ascending order with NaN last (jnp.argsort, env/utils.py:132)
+  const bool nj = aj != aj, nr = ar != ar;
+  if (nj || nr) return (!nj && nr) || (nj && nr && j < r);
+  return (aj < ar) || (aj == ar && j < r);
+}
+
+__global__ void __launch_bounds__(K2_WARPS * 32)
+lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ obstacles,
+             const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long item = (long)blockIdx.x * K2_WARPS + warp;
+  const int n = k.n, R = k.n_rays;
+  if (item >= (long)b * n) return;
+  const int env = (int)(item / n);
+  float* al = smem + warp * (3 * R);
+  float* hx = al + R;
+  float* hy = hx + R;
+
+  const float x1 = agent[item * sd + 0], y1 = agent[item * sd + 1];
+  const float4* ob = reinterpret_cast<const float4*>(obstacles + (size_t)env * k.n_obs * DGPPO_OBS_STRIDE);
+
+  // inside_obstacles(start, r=0): obstacle.py:62-72 with r = 0 reduces to
+  // (rel_xx < 0 && rel_yy < 0); the corner/circle clause needs sqrt(..) < 0.
+  bool in_any = false;
+  for (int o = lane; o < k.n_obs; o += 32) {
+    const float4 a = ob[o * 4 + 0], c = ob[o * 4 + 1];
+    const float rel_x = fsub(x1, a.x), rel_y = fsub(y1, a.y);
+    const float hw = fdiv(a.z, 2.f), hh = fdiv(a.w, 2.f);
+    const float cs = c.y, sn = c.z;
+    const float rxx = fsub(fabsf(fadd(fmul(rel_x, cs), fmul(rel_y, sn))), hw);
+    const float ryy = fsub(fabsf(fsub(fmul(rel_x, sn), fmul(rel_y, cs))), hh);
+    in_any |= (rxx < 0.f) && (ryy < 0.f);
+  }
+  in_any = __any_sync(0xffffffffu, in_any);
+  const float keep = fsub(1.f, in_any ? 1.f : 0.f);
+
+  for (int r = lane; r < R; r += 32) {
+    const float x2 = fadd(x1, ray_dirs[2 * r]), y2 = fadd(y1, ray_dirs[2 * r + 1]);
+    const float dx12 = fsub(x1, x2), dy12 = fsub(y1, y2);
+    float amin = INFINITY;
+    for (int o = 0; o < k.n_obs; ++o) {
+      const float4 p01 = ob[o * 4 + 2], p23 = ob[o * 4 + 3];
+      const float qx[4] = {p01.x, p01.z, p23.x, p23.z};
+      const float qy[4] = {p01.y, p01.w, p23.y, p23.w};
+      float amo = INFINITY;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {                       // obstacle.py:82-104
+        const float x3 = qx[e], y3 = qy[e];
+        const float x4 = qx[(e + 3) & 3], y4 = qy[(e + 3) & 3];
+        const float dx43 = fsub(x4, x3), dy43 = fsub(y4, y3);
+        const float dx13 = fsub(x1, x3), dy13 = fsub(y1, y3);
+        float det = fsub(fmul(dx12, dy43), fmul(dy12, dx43));
+        const float sg = (det > 0.f) ? 1.f : ((det < 0.f) ? -1.f : det);   // sign(0)=0, sign(NaN)=NaN
+        det = fmul(sg, fminf(fmaxf(fabsf(det), 1e-7f), 1e7f));
+        const float alpha = fdiv(fsub(fmul(dy43, dx13), fmul(dx43, dy13)), det);
+        const float beta = fdiv(fadd(fmul(-dy12, dx13), fmul(dx12, dy13)), det);
+        const float vf = (alpha <= 1.f && alpha >= 0.f && beta <= 1.f && beta >= 0.f) ? 1.f : 0.f;
+        const float am = fadd(fmul(vf, alpha), fmul(fsub(1.f, vf), 1e6f));
+        amo = nanmin(amo, am);
+      }
+      amin = nanmin(amin, amo);
+    }
+    const float a = fmul(amin, keep);                      // env/utils.py:129
+    al[r] = a;
+    hx[r] = fadd(x1, fmul(fsub(x2, x1), a));               // env/utils.py:134
+    hy[r] = fadd(y1, fmul(fsub(y2, y1), a));
+  }
+  __syncwarp();
+  float* out = hits + item * k.top_k * 2;
+  for (int r = lane; r < R; r += 32) {
+    const float ar = al[r];
+    int rank = 0;
+    for (int j = 0; j < R; ++j) rank += key_less(al[j], j, ar, r) ? 1 : 0;
+    if (rank < k.top_k) { out[2 * rank] = hx[r]; out[2 * rank + 1] = hy[r]; }
+  }
+}
+
+// ------------------------------------------------------------------- K3
+// One CTA per environment.  Agent / goal / obstacle-node tiles are staged in
+// shared memory; every thread then produces whole output elements (a float4
+// edge row + its receiver/sender, or one node scalar) so all stores are
+// coalesced.
+constexpr int K3_THREADS = 128;
+
+__global__ void __launch_bounds__(K3_THREADS)
+build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
+                   const float* __restrict__ goal, const float* __restrict__ obs_nodes,
+                   float* __restrict__ nodes, float* __restrict__ edges, float* __restrict__ states,
+                   int* __restrict__ receivers, int* __restrict__ senders, int* __restrict__ node_type,
+                   int* __restrict__ n_node, int* __restrict__ n_edge, int pitch, int b) {
+  extern __shared__ float smem[];
+  const int env = blockIdx.x;
+  if (env >= b) return;
+  const int n = d.n, g = d.g, sd = d.sd, nd = d.nd, N = d.N, E = d.E;
+  const bool lid = is_lidar(k.kind), bic = is_bicycle(k.kind);
+  const int ow = lid ? 2 : 4;                    // floats per obstacle node
+  float* sa = smem;                              // agent states   n*sd
+  float* sg = sa + n * sd;                       // goal states    g*sd
+  float* fa = sg + g * sd;                       // agent feats    n*4
+  float* fg = fa + n * 4;                        // goal feats     g*4
+  float* so = fg + g * 4;                        // obstacle nodes n_on*ow
+
+  const float* ag = agent + (size_t)env * n * sd;
+  const float* gl = goal + (size_t)env * g * sd;
+  for (int i = threadIdx.x; i < n * sd; i += K3_THREADS) sa[i] = ag[i];
+  for (int i = threadIdx.x; i < g * sd; i += K3_THREADS) sg[i] = gl[i];
+  if (d.n_on > 0) {
+    const float* on = obs_nodes + (size_t)env * d.n_on * ow;
+    for (int i = threadIdx.x; i < d.n_on * ow; i += K3_THREADS) so[i] = on[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n + g; i += K3_THREADS) {   // state2feat
+    const float* s = (i < n) ? sa + i * sd : sg + (i - n) * sd;
+    float* f = (i < n) ? fa + i * 4 : fg + (i - n) * 4;
+    f[0] = s[0]; f[1] = s[1];
+    if (bic) { f[2] = fmul(s[4], s[2]); f[3] = fmul(s[4], s[3]); }   // lidar_bicycle_target.py:113-118
+    else     { f[2] = s[2]; f[3] = s[3]; }
+  }
+  __syncthreads();
+
+  const size_t slot = (size_t)env * pitch;
+  // nodes (N, nd), states (N, sd), node_type (N): lidar_env/base.py:234-264
+  float* on_ = nodes + slot * N * nd;
+  for (int idx = threadIdx.x; idx < N * nd; idx += K3_THREADS) {
+    const int row = idx / nd, c = idx - row * nd;
+    float v = 0.f;
+    if (row < n)            v = (c < sd) ? sa[row * sd + c] : ((c == sd + 2) ? 1.f : 0.f);
+    else if (row < n + g)   v = (c < sd) ? sg[(row - n) * sd + c] : ((c == sd + 1) ? 1.f : 0.f);
+    else if (row < N - 1) {
+      const int o = row - n - g;
+      v = (c < ow && c < sd) ? so[o * ow + c] : ((c == sd) ? 1.f : 0.f);
+    }
+    on_[idx] = v;
+  }
+  float* os_ = states + slot * N * sd;
+  for (int idx = threadIdx.x; idx < N * sd; idx += K3_THREADS) {
+    const int row = idx / sd, c = idx - row * sd;
+    float v;
+    if (row < n)            v = sa[row * sd + c];
+    else if (row < n + g)   v = sg[(row - n) * sd + c];
+    else if (row < N - 1)   v = (c < ow) ? so[(row - n - g) * ow + c] : 0.f;
+    else                    v = -1.f;                        // utils/graph.py:217
+    os_[idx] = v;
+  }
+  int* ot_ = node_type + slot * N;
+  for (int row = threadIdx.x; row < N; row += K3_THREADS)
+    ot_[row] = (row < n) ? 0 : ((row < n + g) ? 1 : ((row < N - 1) ? 2 : -1));
+  if (threadIdx.x == 0) {
+    if (n_node) n_node[slot] = N;
+    if (n_edge) n_edge[slot] = E;
+  }
+
+  // edges: static slots, [a-a | a-goal | a-obs]; masked slot -> recv=send=pad
+  float4* oe_ = reinterpret_cast<float4*>(edges + slot * E * 4);
+  int* or_ = receivers + slot * E;
+  int* osn_ = senders + slot * E;
+  const int pad = N - 1, nn = n * n, nag = n * d.n_ag;
+  for (int e = threadIdx.x; e < E; e += K3_THREADS) {
+    float4 f; bool m; int rcv, snd;
+    if (e < nn) {                                            // lidar_spread.py:59-67
+      const int i = e / n, j = e - i * n;
+      const float* a = fa + i * 4; const float* c = fa + j * 4;
+      f = make_float4(fsub(a[0], c[0]), fsub(a[1], c[1]), fsub(a[2], c[2]), fsub(a[3], c[3]));
+      float dist = norm2(fsub(sa[i * sd], sa[j * sd]), fsub(sa[i * sd + 1], sa[j * sd + 1]));
+      dist = fadd(dist, (i == j) ? k.R_diag : 0.f);
+      m = dist < k.R; rcv = i; snd = j;
+    } else if (e < nn + nag) {                               // lidar_spread.py:69-76 | lidar_target.py:69-76
+      const int r = e - nn;
+      const int i = (d.n_ag == 1) ? r : r / g;
+      const int q = (d.n_ag == 1) ? r : r - i * g;
+      const float* a = fa + i * 4; const float* c = fg + q * 4;
+      f = make_float4(fsub(a[0], c[0]), fsub(a[1], c[1]), fsub(a[2], c[2]), fsub(a[3], c[3]));
+      m = true; rcv = i; snd = n + q;
+    } else {
+      const int r = e - nn - nag;
+      const int i = r / d.n_ao, q = r - i * d.n_ao;
+      if (lid) {                                             // lidar_spread.py:78-94
+        const float fx = fsub(sa[i * sd], so[r * 2]), fy = fsub(sa[i * sd + 1], so[r * 2 + 1]);
+        f = make_float4(fx, fy, 0.f, 0.f);
+        m = norm2(fx, fy) < k.R_obs; rcv = i; snd = n + g + r;
+      } else {                                               // mpe_spread.py:70-79
+        const float* a = sa + i * sd; const float* c = so + q * 4;
+        f = make_float4(fsub(a[0], c[0]), fsub(a[1], c[1]), fsub(a[2], c[2]), fsub(a[3], c[3]));
+        m = norm2(f.x, f.y) < k.R; rcv = i; snd = n + g + q;
+      }
+    }
+    oe_[e] = f;
+    or_[e] = m ? rcv : pad;
+    osn_[e] = m ? snd : pad;
+  }
+}
+
+}  // namespace dgppo
+
+using namespace dgppo;
+
+extern "C" int dgppo_abi_version(void) { return DGPPO_ABI_VERSION; }
+
+extern "C" int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out) {
+  if (int rc = check_env_cfg(cfg)) return rc;
+  if (!out) return DGPPO_EINVAL;
+  const GraphDims d = graph_dims(*cfg);
+  out->state_dim = d.sd; out->node_dim = d.nd; out->edge_dim = 4;
+  out->n_obs_nodes = d.n_on; out->n_nodes = d.N; out->n_edges = d.E;
+  out->n_ag = d.n_ag; out->n_ao = d.n_ao;
+  return 0;
+}
+
+extern "C" int dgppo_env_step(void* stream, const DgppoEnvCfg* cfg, const float* agent,
+                              const float* goal, const float* obs_nodes, const float* action,
+                              float* next_agent, float* reward, float* cost, int32_t io_pitch, int32_t b) {
+  if (int rc = check_env_cfg(cfg)) return rc;
+  if (b == 0) return 0;
+  if (b < 0 || io_pitch < 1 || !agent || !goal || !action || !next_agent || !reward || !cost) return DGPPO_EINVAL;
+  if (cfg->n_obs > 0 && !obs_nodes) return DGPPO_EINVAL;
+  const EnvConsts k = make_consts(*cfg);
+  const size_t smem = (size_t)K1_WARPS * 5 * k.n * sizeof(float);
+  if (smem > 48 * 1024) return DGPPO_ENOTSUP;
+  const int grid = (b + K1_WARPS - 1) / K1_WARPS;
+  env_step_kernel<<<grid, K1_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      k, agent, goal, obs_nodes, action, next_agent, reward, cost, io_pitch, b);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent,
+                           const float* obstacles, const float* ray_dirs, float* hits, int32_t b) {
+  if (int rc = check_env_cfg(cfg)) return rc;
+  if (!is_lidar(cfg->kind) || cfg->n_obs == 0) return DGPPO_ENOTSUP;
+  if (b == 0) return 0;
+  if (b < 0 || !agent || !obstacles || !ray_dirs || !hits) return DGPPO_EINVAL;
+  const EnvConsts k = make_consts(*cfg);
+  const size_t smem = (size_t)K2_WARPS * 3 * k.n_rays * sizeof(float);
+  const long items = (long)b * k.n;
+  const int grid = (int)((items + K2_WARPS - 1) / K2_WARPS);
+  lidar_kernel<<<grid, K2_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dgppo_build_graph(void* stream, const DgppoEnvCfg* cfg, const float* agent,
+                                 const float* goal, const float* obs_nodes, float* nodes,
+                                 float* edges, float* states, int32_t* receivers, int32_t* senders,
+                                 int32_t* node_type, int32_t* n_node, int32_t* n_edge,
+                                 int32_t pitch, int32_t b) {
+  if (int rc = check_env_cfg(cfg)) return rc;
+  if (b == 0) return 0;
+  if (b < 0 || pitch < 1 || !agent || !goal || !nodes || !edges || !states || !receivers ||
+      !senders || !node_type) return DGPPO_EINVAL;
+  const EnvConsts k = make_consts(*cfg);
+  const GraphDims d = graph_dims(*cfg);
+  if (d.n_on > 0 && !obs_nodes) return DGPPO_EINVAL;
+  const int ow = is_lidar(cfg->kind) ? 2 : 4;
+  const size_t smem = (size_t)(d.n * d.sd + d.g * d.sd + (d.n + d.g) * 4 + d.n_on * ow) * sizeof(float);
+  if (smem > 48 * 1024) return DGPPO_ENOTSUP;
+  build_graph_kernel<<<b, K3_THREADS, smem, (cudaStream_t)stream>>>(
+      k, d, agent, goal, obs_nodes, nodes, edges, states, receivers, senders, node_type,
+      n_node, n_edge, pitch, b);
+  return (int)cudaGetLastError();
+}

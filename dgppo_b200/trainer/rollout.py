@@ -1,0 +1,134 @@
+"""Batched rollout on the B200 kernels.
+
+Replaces `rollout` / `test_rollout` (dgppo/trainer/utils.py:22-86) as they
+are used by `algo.collect` and `DGPPO.det_rollout_fn` (informarl.py:177-186,
+dgppo.py:108-117): one call of `dgppo_rollout` runs the T-step scan for all
+`b` environments of this rank and fills a (b, T+1, ...) record in HBM.
+
+`next_graph[t]` is `graph[t+1]` (trainer/utils.py:48-51), so the record holds
+T+1 graphs once and exposes `graph` / `next_graph` as two views of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from ..env.base import MultiAgentEnv, ptr, stream_ptr
+from ..env.envs import LidarEnv, LidarEnvState, MPEEnvState
+from ..utils.graph import GraphsTuple
+from .data import Rollout
+
+RNN_DIM = 64
+
+
+class RolloutRecord:
+    """Device buffers of one (b, T+1, ...) rollout record + kernel workspaces."""
+
+    def __init__(self, env: MultiAgentEnv, b: int, T: int, device: torch.device, stochastic: bool):
+        d = env.graph_dims()
+        n = env.num_agents
+        self.env, self.b, self.T, self.d, self.n = env, b, T, d, n
+        f32 = dict(dtype=torch.float32, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        P = T + 1
+        self.nodes = torch.empty((b, P, d.n_nodes, d.node_dim), **f32)
+        self.edges = torch.empty((b, P, d.n_edges, 4), **f32)
+        self.states = torch.empty((b, P, d.n_nodes, d.state_dim), **f32)
+        self.receivers = torch.empty((b, P, d.n_edges), **i32)
+        self.senders = torch.empty((b, P, d.n_edges), **i32)
+        self.node_type = torch.empty((b, P, d.n_nodes), **i32)
+        self.n_node = torch.empty((b, P), **i32)
+        self.n_edge = torch.empty((b, P), **i32)
+        self.rnn = torch.empty((b, P, n, RNN_DIM), **f32)
+        self.actions = torch.empty((b, T, n, 2), **f32)
+        self.log_pis = torch.empty((b, T, n), **f32) if stochastic else None
+        self.rewards = torch.empty((b, T), **f32)
+        self.costs = torch.empty((b, T, n, 2), **f32)
+        self.dones = torch.zeros((b, T), dtype=torch.bool, device=device)
+        self.agent_ws = torch.empty((2, b, n, d.state_dim), **f32)
+        self.hits_ws = None
+        if isinstance(env, LidarEnv) and d.n_obs_nodes > 0:
+            self.hits_ws = torch.empty((b, n, env.params["top_k_rays"], 2), **f32)
+
+    def nbytes(self) -> int:
+        ts = [self.nodes, self.edges, self.states, self.receivers, self.senders, self.node_type,
+              self.n_node, self.n_edge, self.rnn, self.actions, self.rewards, self.costs, self.dones]
+        if self.log_pis is not None:
+            ts.append(self.log_pis)
+        return sum(t.numel() * t.element_size() for t in ts)
+
+    def graph_view(self, lo: int, hi: int, env_states) -> GraphsTuple:
+        s = slice(lo, hi)
+        return GraphsTuple(self.n_node[:, s], self.n_edge[:, s], self.nodes[:, s], self.edges[:, s],
+                           self.states[:, s], self.receivers[:, s], self.senders[:, s],
+                           self.node_type[:, s], env_states)
+
+
+def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch.Tensor,
+                graph0: GraphsTuple, eps: Optional[torch.Tensor], T: int,
+                init_rnn_state: Optional[torch.Tensor] = None,
+                record: Optional[RolloutRecord] = None, test_mode: bool = False) -> Rollout:
+    """Run T steps from the batched, already-reset `graph0` (b, ...).
+
+    eps: (b, T, n, 2) N(0,1) draws for the stochastic policy (`algo.step`), or
+    None for the deterministic one (`algo.act`).  test_mode selects
+    `test_rollout`'s convention of emitting the POST-step rnn state
+    (trainer/utils.py:73-77) instead of `rollout`'s pre-step one (:50-51).
+    """
+    b = graph0.nodes.shape[0]
+    dev = graph0.nodes.device
+    n = env.num_agents
+    if record is None:
+        record = RolloutRecord(env, b, T, dev, stochastic=eps is not None)
+    rec, d = record, record.d
+    assert rec.b == b and rec.T == T
+    es = graph0.env_states
+
+    # slot 0 <- the reset graph; workspaces <- the reset state
+    for name in ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge"):
+        getattr(rec, name)[:, 0].copy_(getattr(graph0, name))
+    if init_rnn_state is None:
+        rec.rnn[:, 0].zero_()
+    else:   # (rnn_layers=1, n, n_carries=1, 64) as algo.init_rnn_state (informarl.py:114-124)
+        rec.rnn[:, 0].copy_(init_rnn_state.reshape(n, RNN_DIM).to(dev))
+    rec.agent_ws[0].copy_(es.agent)
+    goal = es.goal.contiguous()
+    obstacles, rays = None, None
+    if isinstance(es, LidarEnvState):
+        if rec.hits_ws is not None:
+            obstacles = es.obstacle.record.contiguous()
+            rays = env.ray_dirs(dev)
+            k = env.params["top_k_rays"]
+            rec.hits_ws.copy_(graph0.states[:, 2 * n:2 * n + n * k, :2].reshape(b, n, k, 2))
+    elif isinstance(es, MPEEnvState) and es.obs is not None:
+        obstacles = es.obs.contiguous()
+    if eps is not None:
+        eps = eps.contiguous()
+        assert eps.shape == (b, T, n, 2) and eps.dtype == torch.float32
+
+    buf = _lib.DgppoRolloutBuffers(
+        ptr(rec.nodes), ptr(rec.edges), ptr(rec.states), ptr(rec.receivers), ptr(rec.senders),
+        ptr(rec.node_type), ptr(rec.n_node), ptr(rec.n_edge), ptr(rec.rnn), ptr(eps),
+        ptr(rec.actions), ptr(rec.log_pis) if eps is not None else None, ptr(rec.rewards), ptr(rec.costs),
+        ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays))
+    cfg = env.env_cfg()
+    _lib.check(_lib.lib().dgppo_rollout(stream_ptr(), C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
+                                         C.byref(buf), T, b), "dgppo_rollout")
+
+    sd = d.state_dim
+    def env_view(lo, hi):
+        st = rec.states[:, lo:hi]
+        if isinstance(es, LidarEnvState):
+            return LidarEnvState(st[:, :, :n], st[:, :, n:2 * n], es.obstacle)
+        return MPEEnvState(st[:, :, :n], st[:, :, n:2 * n], es.obs)
+    rnn = rec.rnn[:, 1:] if test_mode else rec.rnn[:, :T]
+    return Rollout(
+        graph=rec.graph_view(0, T, env_view(0, T)),
+        actions=rec.actions,
+        rnn_states=rnn.unsqueeze(2).unsqueeze(4),           # (b, T, rnn_layers=1, n, n_carries=1, 64)
+        rewards=rec.rewards, costs=rec.costs, dones=rec.dones,
+        log_pis=rec.log_pis if eps is not None else None,
+        next_graph=rec.graph_view(1, T + 1, env_view(1, T + 1)))

@@ -1,0 +1,281 @@
+/*
+ * dgppo_abi.h - C ABI of libdgppo_b200.so, the sm_100a kernel library behind
+ * the DGPPO rollout hot path.
+ *
+ * The reference (syzhang092218-source/dgppo) is pure Python/JAX: it has no
+ * FFI, plugin or operator interface.  Its boundary for this path is the
+ * Python API (env.reset/step/get_graph, algo.act/step/collect/update); every
+ * entry point below names the reference function(s) (file:line under
+ * /root/reference) whose jitted body it replaces.  A JAX host binds these
+ * through XLA-FFI custom calls; this repo's host mirror
+ * (dgppo_b200/) binds them with ctypes on torch device buffers.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every buffer is DEVICE memory owned by
+ *    the caller; no allocation, no retention past the call (the rollout
+ *    orchestrator takes an explicit workspace);
+ *  - every launch is asynchronous on `stream` (a cudaStream_t passed as
+ *    void*), no host synchronisation; re-entrant, no mutable globals;
+ *  - return value: 0 on success, a cudaError_t (>0) from the launch, or a
+ *    negative DGPPO_E* code for arguments the kernels do not support;
+ *  - all arrays are dense row-major fp32 / int32, batched over a leading
+ *    environment axis `b` (the reference batches with jax.vmap:
+ *    dgppo/algo/informarl.py:183-184);
+ *  - graph arrays may live inside a (b, pitch, ...) time-major-per-env
+ *    record (pitch = T+1 for a Rollout buffer, 1 for a plain batch): the
+ *    pointer addresses slot t of env 0 and consecutive envs are
+ *    `pitch * per-graph-size` elements apart.
+ */
+#ifndef DGPPO_ABI_H_
+#define DGPPO_ABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGPPO_ABI_VERSION 1
+
+/* negative error codes (positive values are cudaError_t) */
+#define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
+#define DGPPO_ENOTSUP  (-2)   /* configuration outside what the kernels cover */
+
+/* env kinds (dgppo/env/__init__.py:9-23, the ones on BASELINE.json configs) */
+#define DGPPO_ENV_LIDAR_SPREAD          0  /* lidar_env/lidar_spread.py          */
+#define DGPPO_ENV_LIDAR_TARGET          1  /* lidar_env/lidar_target.py          */
+#define DGPPO_ENV_LIDAR_BICYCLE_TARGET  2  /* lidar_env/lidar_bicycle_target.py  */
+#define DGPPO_ENV_MPE_SPREAD            3  /* mpe/mpe_spread.py                  */
+
+/* Static environment description: the PARAMS dicts (lidar_spread.py:13-22,
+ * mpe_spread.py:12-19) plus dt / num_agents (env/__init__.py:47-53). */
+typedef struct DgppoEnvCfg {
+  int32_t kind;         /* DGPPO_ENV_*                                   */
+  int32_t n_agents;     /* n (== number of goals)                        */
+  int32_t n_obs;        /* rectangles (Lidar*) or circles (MPE*)         */
+  int32_t n_rays;       /* LiDAR beams per agent (default 32)            */
+  int32_t top_k;        /* LiDAR returns kept per agent (default 8)      */
+  int32_t reserved_;    /* keeps the doubles 8-byte aligned              */
+  /* Python floats are doubles: thresholds such as comm_radius - 1e-1,
+   * comm_radius + 1, 2 * car_radius are formed in double and only then
+   * rounded to fp32, as the reference's weak-typed scalars are.          */
+  double comm_radius;   /* 0.5 (area*10 under --full-observation)        */
+  double car_radius;    /* 0.05                                          */
+  double obs_radius;    /* 0.05 (MPE only)                               */
+  double area_size;     /* 1.5                                           */
+  double dt;            /* 0.03                                          */
+  double dist2goal;     /* 0.01                                          */
+} DgppoEnvCfg;
+
+/* Derived graph sizes (utils/graph.py:212-247 + each env's edge_blocks). */
+typedef struct DgppoGraphDims {
+  int32_t state_dim;    /* 4, or 5 for the bicycle                        */
+  int32_t node_dim;     /* state_dim + 3                                  */
+  int32_t edge_dim;     /* 4                                              */
+  int32_t n_obs_nodes;  /* top_k*n hit nodes (Lidar) or n_obs (MPE)       */
+  int32_t n_nodes;      /* n + n_goal + n_obs_nodes + 1 (pad)             */
+  int32_t n_edges;      /* n*n + n*n_ag + n*n_ao                          */
+  int32_t n_ag;         /* goal senders per agent: n (Spread) or 1        */
+  int32_t n_ao;         /* obstacle senders per agent: top_k | n_obs | 0  */
+} DgppoGraphDims;
+
+int dgppo_abi_version(void);
+int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out);
+
+/* Obstacle record, 16 floats per rectangle (Rectangle, env/obstacle.py:30-56):
+ *   [cx, cy, width, height, theta, cos(theta), sin(theta), 0,
+ *    p0x, p0y, p1x, p1y, p2x, p2y, p3x, p3y]
+ * cos/sin are carried as data (obstacle.py:65-66 re-evaluates them per call). */
+#define DGPPO_OBS_STRIDE 16
+
+/* ---- K1: dynamics + reward + cost ------------------------------------
+ * Replaces the arithmetic of LidarEnv.step / MPE.step minus LiDAR and graph
+ * build: clip_action + agent_step_euler + clip_state
+ * (lidar_env/base.py:142-149,160-161; mpe/base.py:129-135,146-147;
+ * lidar_bicycle_target.py:92-111; env/base.py:80-86), get_reward
+ * (lidar_spread.py:35-52, lidar_target.py:35-52, mpe_spread.py:32-49) and
+ * get_cost (lidar_env/base.py:180-207, mpe/base.py:164-191), the last two on
+ * the PRE-step state.
+ *   agent      (b, n, state_dim)      current agent states
+ *   goal       (b, n, state_dim)
+ *   obs_nodes  Lidar: (b, n, top_k, 2) hit points stored in the current graph
+ *              MPE:   (b, n_obs, 4) obstacle states; NULL iff n_obs == 0
+ *   action     (b, io_pitch, n, 2)    unclipped; slot pointer (io_pitch = T
+ *                                     inside a Rollout record, 1 for a batch)
+ *   next_agent (b, n, state_dim)  out
+ *   reward     (b, io_pitch)      out, slot pointer
+ *   cost       (b, io_pitch, n, 2) out, slot pointer                        */
+int dgppo_env_step(void* stream, const DgppoEnvCfg* cfg,
+                   const float* agent, const float* goal, const float* obs_nodes,
+                   const float* action,
+                   float* next_agent, float* reward, float* cost,
+                   int32_t io_pitch, int32_t b);
+
+/* ---- K2: LiDAR ----------------------------------------------------------
+ * get_lidar_data -> get_lidar -> raytracing -> Rectangle.raytracing/inside
+ * (lidar_env/base.py:126-140, env/utils.py:49-79,82-136, obstacle.py:62-105).
+ *   agent     (b, n, state_dim)  positions are columns 0:2
+ *   obstacles (b, n_obs, DGPPO_OBS_STRIDE)
+ *   ray_dirs  (n_rays, 2)  end-point offsets (cos, sin)(theta_r) * comm_radius
+ *   hits      (b, n, top_k, 2) out: the top_k smallest-alpha hit points in
+ *             stable ascending-alpha order (jnp.argsort, env/utils.py:132)    */
+int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg,
+                const float* agent, const float* obstacles, const float* ray_dirs,
+                float* hits, int32_t b);
+
+/* ---- K3: radius graph ----------------------------------------------------
+ * get_graph + edge_blocks + EdgeBlock.make_edges + GetGraph.to_padded
+ * (lidar_env/base.py:227-271, mpe/base.py:211-241, lidar_spread.py:57-96,
+ * lidar_target.py:57-96, lidar_bicycle_target.py:113-118, mpe_spread.py:51-81,
+ * utils/graph.py:35-44,212-247).  Outputs are the GraphsTuple array fields
+ * (utils/graph.py:61-86) for slot `t` of a (b, pitch, ...) record:
+ *   nodes (N, node_dim) f32, edges (E, 4) f32, states (N, state_dim) f32,
+ *   receivers / senders (E) i32, node_type (N) i32, n_node / n_edge () i32
+ * (n_node / n_edge may be NULL).                                            */
+int dgppo_build_graph(void* stream, const DgppoEnvCfg* cfg,
+                      const float* agent, const float* goal, const float* obs_nodes,
+                      float* nodes, float* edges, float* states,
+                      int32_t* receivers, int32_t* senders, int32_t* node_type,
+                      int32_t* n_node, int32_t* n_edge,
+                      int32_t pitch, int32_t b);
+
+/* ---- networks ------------------------------------------------------------ */
+#define DGPPO_NET_POLICY 0   /* PPOPolicy / TanhNormal   (algo/module/policy.py:20-78,132-212) */
+#define DGPPO_NET_VH     1   /* DecRStateFn, per-agent   (algo/module/value.py:47-79)          */
+#define DGPPO_NET_VL     2   /* RStateFn, mean-pooled    (algo/module/value.py:15-44)          */
+
+typedef struct DgppoNetCfg {
+  int32_t kind;       /* DGPPO_NET_*                                          */
+  int32_t node_dim;   /* 7 | 8                                                */
+  int32_t edge_dim;   /* 4                                                    */
+  int32_t n_layers;   /* GraphTransformer layers: 2 (policy, Vl) | 1 (Vh)     */
+  int32_t n_out;      /* action_dim (2) | n_cost (2) | 1                      */
+} DgppoNetCfg;
+
+/* Offsets (in floats) of each block in the packed parameter buffer.
+ * Fixed widths follow the reference: msg_dim 32, gnn_out_dim 64, H = 3 heads,
+ * head MLP (64,64), GRU 64 (policy.py:149-169, informarl.py:102-112,
+ * dgppo.py:83-95).  The buffer is a DEVICE layout, produced from the
+ * reference's flax pytree by dgppo_b200.algo.params.pack_params (or any host
+ * following this description).  flax kernels are (in, out) row-major; with
+ * IN = layer input width, D = layer output width, HD = H*D and the
+ * GraphTransformer denses named as flax auto-names them (gnn.py:86-98,110:
+ * Dense_0 query on receivers, Dense_1 key on senders, Dense_2 value on
+ * senders, Dense_3 edge without bias, Dense_4 update), layer l holds
+ *   wq   [IN][HD]      = Dense_0.kernel             bq [HD] = Dense_0.bias
+ *   wkt  [H][D][INP]   key, transposed per head with the bias folded in:
+ *                        wkt[h][j][c] = Dense_1.kernel[c][h*D+j]  (c <  IN)
+ *                                     = Dense_1.bias[h*D+j]       (c == IN)
+ *                                     = 0                         (c >  IN)
+ *                        INP = round_up(IN + 1, 4)
+ *   wagg [H][INA][D]   value / edge, grouped per head, INA = IN + 1 + 4:
+ *                        wagg[h][c][j] = Dense_2.kernel[c][h*D+j]      (c < IN)
+ *                                      = Dense_2.bias[h*D+j]           (c == IN)
+ *                                      = Dense_3.kernel[c-IN-1][h*D+j] (c > IN)
+ *   wu   [IN][D]       = Dense_4.kernel             bu [D] = Dense_4.bias
+ * (the kernels evaluate the attention in the algebraically regrouped form
+ *  score = (Wk^T q) . x_s + q . bk,  agg = sum_h Wv_h (sum_e a_e x_s) + ...,
+ *  DESIGN.md "GNN regrouping").
+ * Head (mlp.py:14-30): d0w [64][64], d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b.
+ * GRU (flax GRUCell): wi = [ir|iz|in].kernel (64,192), bi = their biases
+ *   (192), wh = [hr|hz|hn].kernel (64,192), bhn = hn.bias (64).
+ * Tail: policy: scale_w [64][64], scale_b = ScaleHid; out_w [64][4] =
+ *   [OutputDenseMean | OutputDenseStdTrans] (n_out = 2), out_b [4].
+ *   value: out_w [64][4] = Dense_0.kernel zero-padded to 4 columns, out_b [4]. */
+typedef struct DgppoNetLayout {
+  int32_t wq[2], bq[2], wkt[2], wagg[2], wu[2], bu[2];
+  int32_t in_dim[2], out_dim[2];
+  int32_t d0w, d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b;
+  int32_t wi, bi, wh, bhn;
+  int32_t scale_w, scale_b, out_w, out_b;
+  int32_t total;      /* floats in the packed buffer */
+} DgppoNetLayout;
+
+int dgppo_net_layout(const DgppoNetCfg* net, DgppoNetLayout* out);
+
+/* ---- K4a: policy forward + sample -------------------------------------
+ * InforMARL.step / act (algo/informarl.py:230-252) ->
+ * PPOPolicy.sample_action / get_action (policy.py:191-203) ->
+ * TanhNormal (policy.py:61-74) -> PolicyNet (policy.py:25-33) ->
+ * GraphTransformerGNN (nn/gnn.py:78-142), MLP (nn/mlp.py:14-30),
+ * RNN/GRUCell (nn/rnn.py:14-30), TanhTransformedDistribution
+ * (algo/module/distribution.py:10-46).
+ *   params  packed per dgppo_net_layout
+ *   nodes/edges/receivers/senders  graph slot (see pitch)
+ *   rnn_in  (b, rnn_pitch, n, 64) slot pointer;  rnn_out likewise
+ *   eps     (b, eps_pitch, n, 2) slot pointer of N(0,1) draws, or NULL for
+ *           the deterministic mode tanh(mean)
+ *   action  (b, act_pitch, n, 2) slot pointer out
+ *   log_pi  (b, act_pitch, n)   slot pointer out (NULL allowed when eps NULL) */
+int dgppo_gnn_policy(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                     const float* params,
+                     const float* nodes, const float* edges,
+                     const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                     const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                     const float* eps, int32_t eps_pitch,
+                     float* action, float* log_pi, int32_t act_pitch, int32_t b);
+
+/* ---- K4b: value forward -------------------------------------------------
+ * DGPPO.get_Vh -> ValueNet.get_value -> DecRStateFn (dgppo.py:128-134,
+ * value.py:47-79,155-157) for kind VH: the GRU carry is the policy's stored
+ * rnn state (n rows per env), output (b, out_pitch, n, n_out).
+ * Kind VL (RStateFn, value.py:15-44): mean over agents, one GRU row per env:
+ * rnn_in/rnn_out (b, rnn_pitch, 64), output (b, out_pitch).
+ * The whole (b, pitch) record is evaluated in one call when n_slots > 1:
+ * slots 0..n_slots-1 of every env (Vh over all (b,T): dgppo.py:219-220).     */
+int dgppo_gnn_value(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                    const float* params,
+                    const float* nodes, const float* edges,
+                    const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                    const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                    float* value, int32_t out_pitch, int32_t n_slots, int32_t b);
+
+/* ---- K5: GAE ---------------------------------------------------------------
+ * compute_dec_ocp_gae (algo/utils.py:11-79; callers dgppo.py:232-237,268-273).
+ *   hs (b,T,n,nh) costs, l (b,T) = -rewards, Vh (b,T+1,n,nh), Vl (b,T+1)
+ *   -> Qh (b,T,n,nh), Ql (b,T)                                               */
+int dgppo_gae(void* stream, const float* hs, const float* l, const float* Vh, const float* Vl,
+              float gamma, float gae_lambda, float* Qh, float* Ql,
+              int32_t b, int32_t T, int32_t n, int32_t nh);
+
+/* ---- CBF residual + advantage merge (dgppo.py:239-259) --------------------
+ *   Ql (b,T), Vl (b,T+1), Vh (b,T+1,n,nh)
+ *   -> A (b,T,n) [= -(safe ? Al_hat : 0) - max_h Acbf * cbf_weight],
+ *      cbf_deriv (b,T,n,nh), Acbf (b,T,n,nh) (either may be NULL),
+ *      is_safe (b,T,n) u8 (may be NULL)                                      */
+int dgppo_cbf_advantage(void* stream, const float* Ql, const float* Vl, const float* Vh,
+                        float dt, float alpha, float cbf_eps, float cbf_weight,
+                        float* A, float* cbf_deriv, float* Acbf, uint8_t* is_safe,
+                        int32_t b, int32_t T, int32_t n, int32_t nh);
+
+/* ---- fused rollout -----------------------------------------------------------
+ * rollout / test_rollout scan (trainer/utils.py:45-57,70-86) behind
+ * algo.collect / det_rollout_fn (informarl.py:177-186,254-256,
+ * dgppo.py:108-117,141), from an already-reset batch: slot 0 of the graph
+ * record and of `agent` hold the initial state.  Runs T x {policy, step,
+ * LiDAR, graph} on `stream` with no host synchronisation.
+ * The record is (b, T+1, ...) per graph field (graph = [:, :T], next_graph =
+ * [:, 1:]); rnn (b, T+1, n, 64) (rollout emits [:, :T], test_rollout [:, 1:]);
+ * eps (b, T, n, 2) or NULL (deterministic); actions (b,T,n,2), log_pis (b,T,n)
+ * (NULL allowed iff eps NULL), rewards (b,T), costs (b,T,n,2).
+ * agent_ws: workspace (2, b, n, state_dim) ping-pong agent states, slot 0
+ * initialised by the caller; hits_ws (b, n, top_k, 2) (Lidar) initialised
+ * with the hits of the initial state.                                        */
+typedef struct DgppoRolloutBuffers {
+  float* nodes; float* edges; float* states;
+  int32_t* receivers; int32_t* senders; int32_t* node_type;
+  int32_t* n_node; int32_t* n_edge;
+  float* rnn; const float* eps;
+  float* actions; float* log_pis; float* rewards; float* costs;
+  float* agent_ws; float* hits_ws;
+  const float* goal; const float* obstacles; const float* ray_dirs;
+} DgppoRolloutBuffers;
+
+int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                  const float* params, const DgppoRolloutBuffers* buf,
+                  int32_t T, int32_t b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DGPPO_ABI_H_ */

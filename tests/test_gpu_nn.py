@@ -1,0 +1,107 @@
+"""GPU parity of K4 (policy / Vh / Vl forward) against the oracle through the
+C ABI.  Tolerance: north_star's rtol 1e-5 (fp32), with an absolute floor of
+1e-5 x the output scale for values near zero; the fp64 oracle is the yardstick
+showing the CUDA error is of the size of fp32 rounding noise."""
+import numpy as np
+import pytest
+
+from dgppo_b200 import _lib
+from dgppo_b200.algo import params as P
+from oracle import env_np, nn_np
+from tests import util
+from tests.util import CONFIGS
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _graph(cfg, b, seed):
+    agent, goal, obstacles, mpe_obs = util.threshold_states(cfg, b, seed)
+    return env_np.reset_graph(cfg, agent, goal, obstacles, mpe_obs)
+
+
+def _close(got, ref32, ref64, what):
+    scale = max(1.0, float(np.abs(ref64).max()))
+    err = np.abs(got.astype(np.float64) - ref64)
+    err32 = np.abs(ref32.astype(np.float64) - ref64)
+    msg = f"{what}: max err vs fp64 {err.max():.3e} (oracle fp32's own {err32.max():.3e}), scale {scale:.3g}"
+    print(msg)
+    np.testing.assert_allclose(got, ref32, rtol=RTOL, atol=ATOL * scale, err_msg=msg)
+    assert err.max() <= 20 * max(err32.max(), 1e-7 * scale) + ATOL * scale * 0.1, msg
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5", "target", "noobs_lidar", "one_agent"])
+@pytest.mark.parametrize("stochastic", [True, False])
+def test_policy_forward(name, stochastic):
+    cfg = CONFIGS[name]
+    b = 5 if cfg.n >= 64 else 37           # not a multiple of the tile size
+    g = _graph(cfg, b, 21)
+    tree = P.init_policy_params(cfg.node_dim, 4, 2, 2, seed=3, jitter=0.1, scale_final=1.0)
+    nc = P.net_cfg(_lib.NET_POLICY, cfg.node_dim, 4, 2, 2)
+    packed = P.pack_params(tree, nc)
+    rng = np.random.default_rng(4)
+    rnn = rng.standard_normal((b, cfg.n, 64)).astype(F) * 0.5
+    eps = rng.standard_normal((b, cfg.n, 2)).astype(F) if stochastic else None
+    a32, lp32, h32, _ = nn_np.policy_forward(tree, g, rnn, cfg.n, eps, 2, np.float32)
+    a64, lp64, h64, _ = nn_np.policy_forward(tree, g, rnn, cfg.n, eps, 2, np.float64)
+    a, lp, h = util.k_policy(cfg, nc, packed, g, rnn, eps)
+    _close(h, h32, h64, f"rnn {name}")
+    _close(a, a32, a64, f"action {name}")
+    if stochastic:
+        _close(lp, lp32, lp64, f"log_pi {name}")
+
+
+def test_policy_log_prob_tails():
+    """Actions that saturate |a| >= 0.999 take the log-cdf branches
+    (distribution.py:25-35)."""
+    cfg = CONFIGS["C1"]
+    b = 16
+    g = _graph(cfg, b, 5)
+    tree = P.init_policy_params(cfg.node_dim, 4, 2, 2, seed=9, jitter=0.1, scale_final=1.0)
+    tree["params"]["OutputDenseMean"]["kernel"] = tree["params"]["OutputDenseMean"]["kernel"] * 40.0
+    nc = P.net_cfg(_lib.NET_POLICY, cfg.node_dim, 4, 2, 2)
+    packed = P.pack_params(tree, nc)
+    rng = np.random.default_rng(1)
+    rnn = rng.standard_normal((b, cfg.n, 64)).astype(F)
+    eps = rng.standard_normal((b, cfg.n, 2)).astype(F)
+    a32, lp32, _, _ = nn_np.policy_forward(tree, g, rnn, cfg.n, eps, 2, np.float32)
+    assert (np.abs(a32) >= 0.999).any(), "test premise: some actions saturate"
+    a, lp, _ = util.k_policy(cfg, nc, packed, g, rnn, eps)
+    np.testing.assert_allclose(a, a32, rtol=1e-5, atol=1e-5)
+    sat = (np.abs(a32) >= 0.999).any(-1) | (np.abs(a) >= 0.999).any(-1)
+    np.testing.assert_allclose(lp[~sat], lp32[~sat], rtol=1e-4, atol=1e-4)
+    # on saturated entries both must take the same branch unless a sits on the threshold
+    agree = np.isclose(lp[sat], lp32[sat], rtol=1e-3, atol=1e-3)
+    assert agree.mean() > 0.9
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5"])
+def test_vh_forward(name):
+    cfg = CONFIGS[name]
+    b = 5 if cfg.n >= 64 else 37
+    g = _graph(cfg, b, 31)
+    tree = P.init_value_params(cfg.node_dim, 4, 2, 1, seed=5, jitter=0.1)
+    nc = P.net_cfg(_lib.NET_VH, cfg.node_dim, 4, 1, 2)
+    packed = P.pack_params(tree, nc)
+    rnn = np.random.default_rng(2).standard_normal((b, cfg.n, 64)).astype(F) * 0.5
+    v32 = nn_np.vh_forward(tree, g, rnn, cfg.n, 1, np.float32)
+    v64 = nn_np.vh_forward(tree, g, rnn, cfg.n, 1, np.float64)
+    v, _ = util.k_value(cfg, nc, packed, g, rnn)
+    _close(v, v32, v64, f"Vh {name}")
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
+def test_vl_forward(name):
+    cfg = CONFIGS[name]
+    b = 37
+    g = _graph(cfg, b, 41)
+    tree = P.init_value_params(cfg.node_dim, 4, 1, 2, seed=6, jitter=0.1)
+    nc = P.net_cfg(_lib.NET_VL, cfg.node_dim, 4, 2, 1)
+    packed = P.pack_params(tree, nc)
+    rnn = np.random.default_rng(3).standard_normal((b, 64)).astype(F) * 0.5
+    v32, h32 = nn_np.vl_forward(tree, g, rnn, cfg.n, 2, np.float32)
+    v64, h64 = nn_np.vl_forward(tree, g, rnn, cfg.n, 2, np.float64)
+    v, h = util.k_value(cfg, nc, packed, g, rnn)
+    _close(v, v32, v64, f"Vl {name}")
+    _close(h, h32, h64, f"Vl carry {name}")
