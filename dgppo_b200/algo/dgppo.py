@@ -244,10 +244,12 @@ class DGPPO(Algorithm):
         rnn_in = rnn_state.reshape(b, n, RNN_DIM).contiguous().float()
         Vh = torch.empty((b, n, self._env.n_cost), dtype=torch.float32, device=rnn_in.device)
         cfg = self._env.env_cfg()
+        nodes, edges = g.nodes.contiguous(), g.edges.contiguous()
+        recv, send = g.receivers.contiguous(), g.senders.contiguous()
         _lib.check(_lib.lib().dgppo_gnn_value(
             stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
-            ptr(g.nodes.contiguous()), ptr(g.edges.contiguous()), ptr(g.receivers.contiguous()),
-            ptr(g.senders.contiguous()), 1, ptr(rnn_in), None, 1, ptr(Vh), 1, 1, b), "dgppo_gnn_value")
+            ptr(nodes), ptr(edges), ptr(recv), ptr(send), 1, ptr(rnn_in), None, 1, ptr(Vh), 1, 1, b),
+            "dgppo_gnn_value")
         return Vh[0] if single else Vh
 
     def scan_Vl(self, rollout: Rollout, params: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -278,9 +280,9 @@ class DGPPO(Algorithm):
         b, T, n, nh = costs.shape
         Qh = torch.empty_like(costs)
         Ql = torch.empty((b, T), dtype=torch.float32, device=costs.device)
-        _lib.check(_lib.lib().dgppo_gae(stream_ptr(), ptr(costs.contiguous()), ptr(neg_rewards.contiguous()),
-                                         ptr(Vh.contiguous()), ptr(Vl.contiguous()), self.gamma, self.gae_lambda,
-                                         ptr(Qh), ptr(Ql), b, T, n, nh), "dgppo_gae")
+        costs, neg_rewards, Vh, Vl = costs.contiguous(), neg_rewards.contiguous(), Vh.contiguous(), Vl.contiguous()
+        _lib.check(_lib.lib().dgppo_gae(stream_ptr(), ptr(costs), ptr(neg_rewards), ptr(Vh), ptr(Vl),
+                                         self.gamma, self.gae_lambda, ptr(Qh), ptr(Ql), b, T, n, nh), "dgppo_gae")
         return Qh, Ql
 
     def cbf_advantage(self, Ql, Vl, Vh, step: int):
@@ -293,8 +295,9 @@ class DGPPO(Algorithm):
         acbf = torch.empty_like(deriv)
         safe = torch.empty((b, T, n), dtype=torch.uint8, device=dev)
         w = self.cbf_schedule_fn(step) if self.cbf_schedule else self.cbf_weight
+        Ql, Vl, Vh = Ql.contiguous(), Vl.contiguous(), Vh.contiguous()
         _lib.check(_lib.lib().dgppo_cbf_advantage(
-            stream_ptr(), ptr(Ql.contiguous()), ptr(Vl.contiguous()), ptr(Vh.contiguous()),
+            stream_ptr(), ptr(Ql), ptr(Vl), ptr(Vh),
             float(self._env.dt), float(self.alpha), float(self.cbf_eps), float(w),
             ptr(A), ptr(deriv), ptr(acbf), ptr(safe), b, T, n, nh), "dgppo_cbf_advantage")
         return A, deriv, acbf, safe.bool()

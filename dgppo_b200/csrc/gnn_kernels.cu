@@ -503,7 +503,7 @@ gnn_forward_kernel(NetP net, GnnArgs g, int m_cap) {
         const float m0 = q[0 * RS + r], m1 = q[1 * RS + r];
         const size_t ao = ((size_t)env * g.act_pitch + slot) * n + i;
         if (g.eps) {
-          const float inv = 0.5413248546129181f;       // log(exp(0.5) - 1)  (policy.py:54-59)
+          const float inv = -0.43275212956718856f;     // log(exp(0.5) - 1)  (policy.py:54-59)
           const float s0 = softplusf_(q[2 * RS + r] + inv) + 1e-5f;
           const float s1 = softplusf_(q[3 * RS + r] + inv) + 1e-5f;
           const float* ep = g.eps + (((size_t)env * g.eps_pitch + slot) * n + i) * 2;

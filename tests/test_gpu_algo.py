@@ -29,7 +29,8 @@ def test_gae(b, T, n, nh):
     hs, l, Vh, Vl = _gae_inputs(b, T, n, nh, 0)
     Qh = torch.empty((b, T, n, nh), device="cuda")
     Ql = torch.empty((b, T), device="cuda")
-    rc = _lib.lib().dgppo_gae(stream(), p(dev(hs)), p(dev(l)), p(dev(Vh)), p(dev(Vl)), 0.99, 0.95, p(Qh), p(Ql),
+    d_hs, d_l, d_Vh, d_Vl = dev(hs), dev(l), dev(Vh), dev(Vl)      # keep the device tensors alive
+    rc = _lib.lib().dgppo_gae(stream(), p(d_hs), p(d_l), p(d_Vh), p(d_Vl), 0.99, 0.95, p(Qh), p(Ql),
                               b, T, n, nh)
     assert rc == 0
     torch.cuda.synchronize()
@@ -54,7 +55,8 @@ def test_cbf_advantage():
     d = torch.empty((b, T, n, nh), device="cuda")
     ac = torch.empty_like(d)
     sf = torch.empty((b, T, n), dtype=torch.uint8, device="cuda")
-    rc = _lib.lib().dgppo_cbf_advantage(stream(), p(dev(Ql)), p(dev(Vl)), p(dev(Vh)), 0.03, 10.0, 1e-2, 2.0,
+    d_Ql, d_Vl, d_Vh = dev(Ql), dev(Vl), dev(Vh)                    # keep the device tensors alive
+    rc = _lib.lib().dgppo_cbf_advantage(stream(), p(d_Ql), p(d_Vl), p(d_Vh), 0.03, 10.0, 1e-2, 2.0,
                                         p(A), p(d), p(ac), p(sf), b, T, n, nh)
     assert rc == 0
     torch.cuda.synchronize()

@@ -42,9 +42,12 @@ def test_lidar_parallel_ray_nan():
     agent[0, 0, :2] = [0.5, 0.75]     # ray 16 (theta = 0) is parallel to the horizontal edges
     agent[0, 1, :2] = [1.0, 0.3]
     rays = env_np.ray_table(32, 0.5)
+    rays[16] = [0.5, 0.0]             # the table is data: make beam 16 exactly horizontal
     ref = env_np.lidar_hits(cfg, agent[..., :2], obstacles, rays)
     got = util.k_lidar(cfg, agent, obstacles, rays)
-    assert np.isnan(ref).any(), "test premise: the oracle produces a NaN hit here"
+    al = env_np.lidar_alphas(agent[..., :2], obstacles, rays)
+    assert np.isnan(al[0, 0, 16]), "test premise: beam 16 of agent 0 has a NaN alpha"
+    assert not np.isnan(ref).any()    # NaN sorts last, so the head-on beam drops out of the top-k
     assert_bits_equal(got, ref, "lidar hits with NaN")
 
 
