@@ -74,7 +74,10 @@ SIGNATURES = {
     "dgppo_cbf_advantage": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float,
                                       _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dgppo_rollout": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
-                                C.POINTER(DgppoRolloutBuffers), C.c_int32, C.c_int32]),
+                                C.POINTER(DgppoRolloutBuffers), C.c_int32, C.c_int32, _fp]),
+    "dgppo_prof_create": (_fp, [C.c_int32]),
+    "dgppo_prof_destroy": (None, [_fp]),
+    "dgppo_prof_read": (C.c_int, [_fp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -174,7 +174,7 @@ class DGPPO(Algorithm):
 
     # ------------------------------------------------------------------ rollouts
     def collect(self, params: dict, b_key, eps: Optional[torch.Tensor] = None, graph0: Optional[GraphsTuple] = None,
-                record=None) -> Rollout:
+                record=None, prof=None) -> Rollout:
         """InforMARL.collect (informarl.py:254-256): jit(vmap(rollout)) over the
         env keys == one batched rollout.  `b_key`: one key per environment."""
         if graph0 is None:
@@ -183,7 +183,7 @@ class DGPPO(Algorithm):
         if eps is None:
             eps = self._eps_from_key(b_key, (b, T, self.n_agents, self.action_dim))
         return run_rollout(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
-                           self.init_rnn_state, record=record)
+                           self.init_rnn_state, record=record, prof=prof)
 
     def det_rollout_fn(self, params: dict, b_key, graph0: Optional[GraphsTuple] = None, record=None) -> Rollout:
         """DGPPO.det_rollout_fn (dgppo.py:108-117): test_rollout with algo.act."""

@@ -6,10 +6,58 @@
 // benchmark sizes, so the host runs ahead of the device.
 #include "common.cuh"
 
+#include <vector>
+
 using namespace dgppo;
 
+// Optional per-kernel timing: cudaEvents recorded on the rollout's own stream
+// around each of the 4 kernels of every step (no synchronisation until read).
+struct DgppoProf {
+  int T;
+  std::vector<cudaEvent_t> ev;     // [T][5]: before policy, after policy, after step, after lidar, after graph
+  bool recorded;
+};
+
+extern "C" void* dgppo_prof_create(int32_t T) {
+  if (T < 1) return nullptr;
+  DgppoProf* p = new DgppoProf{T, std::vector<cudaEvent_t>((size_t)T * 5), false};
+  for (auto& e : p->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { delete p; return nullptr; }
+  return p;
+}
+
+extern "C" void dgppo_prof_destroy(void* prof) {
+  DgppoProf* p = (DgppoProf*)prof;
+  if (!p) return;
+  for (auto& e : p->ev) cudaEventDestroy(e);
+  delete p;
+}
+
+extern "C" int dgppo_prof_read(void* prof, float* ms_sum4, float* ms_max4) {
+  DgppoProf* p = (DgppoProf*)prof;
+  if (!p || !ms_sum4 || !p->recorded) return DGPPO_EINVAL;
+  cudaError_t err = cudaEventSynchronize(p->ev.back());
+  if (err != cudaSuccess) return (int)err;
+  for (int k = 0; k < 4; ++k) { ms_sum4[k] = 0.f; if (ms_max4) ms_max4[k] = 0.f; }
+  for (int t = 0; t < p->T; ++t)
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      err = cudaEventElapsedTime(&ms, p->ev[(size_t)t * 5 + k], p->ev[(size_t)t * 5 + k + 1]);
+      if (err != cudaSuccess) return (int)err;
+      ms_sum4[k] += ms;
+      if (ms_max4 && ms > ms_max4[k]) ms_max4[k] = ms;
+    }
+  return 0;
+}
+
 extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
-                             const float* params, const DgppoRolloutBuffers* B, int32_t T, int32_t b) {
+                             const float* params, const DgppoRolloutBuffers* B, int32_t T, int32_t b,
+                             void* prof_) {
+  DgppoProf* prof = (DgppoProf*)prof_;
+  if (prof && prof->T != T) return DGPPO_EINVAL;
+  auto mark = [&](int t, int k) {
+    if (prof) cudaEventRecord(prof->ev[(size_t)t * 5 + k], (cudaStream_t)stream);
+  };
   if (int rc = check_env_cfg(env)) return rc;
   if (!net || !params || !B || T < 1 || b < 0) return DGPPO_EINVAL;
   if (b == 0) return 0;
@@ -26,6 +74,7 @@ extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNe
     const float* agent_cur = B->agent_ws + (size_t)(t & 1) * agent_sz;
     float* agent_nxt = B->agent_ws + (size_t)((t + 1) & 1) * agent_sz;
     const float* obs_nodes = (d.n_on == 0) ? nullptr : (lid ? B->hits_ws : B->obstacles);
+    mark(t, 0);
     int rc = dgppo_gnn_policy(stream, env, net, params,
                               B->nodes + (size_t)t * d.N * d.nd, B->edges + (size_t)t * d.E * 4,
                               B->receivers + (size_t)t * d.E, B->senders + (size_t)t * d.E, P,
@@ -34,13 +83,16 @@ extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNe
                               B->actions + (size_t)t * n * 2,
                               B->log_pis ? B->log_pis + (size_t)t * n : nullptr, T, b);
     if (rc) return rc;
+    mark(t, 1);
     rc = dgppo_env_step(stream, env, agent_cur, B->goal, obs_nodes, B->actions + (size_t)t * n * 2,
                         agent_nxt, B->rewards + t, B->costs + (size_t)t * n * 2, T, b);
     if (rc) return rc;
+    mark(t, 2);
     if (lid && d.n_on > 0) {
       rc = dgppo_lidar(stream, env, agent_nxt, B->obstacles, B->ray_dirs, B->hits_ws, b);
       if (rc) return rc;
     }
+    mark(t, 3);
     rc = dgppo_build_graph(stream, env, agent_nxt, B->goal, obs_nodes,
                            B->nodes + (size_t)(t + 1) * d.N * d.nd, B->edges + (size_t)(t + 1) * d.E * 4,
                            B->states + (size_t)(t + 1) * d.N * d.sd,
@@ -49,6 +101,8 @@ extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNe
                            B->n_node ? B->n_node + (t + 1) : nullptr,
                            B->n_edge ? B->n_edge + (t + 1) : nullptr, P, b);
     if (rc) return rc;
+    mark(t, 4);
   }
+  if (prof) prof->recorded = true;
   return 0;
 }

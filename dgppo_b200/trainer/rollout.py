@@ -70,7 +70,8 @@ class RolloutRecord:
 def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch.Tensor,
                 graph0: GraphsTuple, eps: Optional[torch.Tensor], T: int,
                 init_rnn_state: Optional[torch.Tensor] = None,
-                record: Optional[RolloutRecord] = None, test_mode: bool = False) -> Rollout:
+                record: Optional[RolloutRecord] = None, test_mode: bool = False,
+                prof=None) -> Rollout:
     """Run T steps from the batched, already-reset `graph0` (b, ...).
 
     eps: (b, T, n, 2) N(0,1) draws for the stochastic policy (`algo.step`), or
@@ -116,7 +117,7 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
         ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays))
     cfg = env.env_cfg()
     _lib.check(_lib.lib().dgppo_rollout(stream_ptr(), C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
-                                         C.byref(buf), T, b), "dgppo_rollout")
+                                         C.byref(buf), T, b, prof), "dgppo_rollout")
 
     sd = d.state_dim
     def env_view(lo, hi):

@@ -273,7 +273,17 @@ typedef struct DgppoRolloutBuffers {
 
 int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
                   const float* params, const DgppoRolloutBuffers* buf,
-                  int32_t T, int32_t b);
+                  int32_t T, int32_t b, void* prof /* nullable */);
+
+/* Optional per-kernel timing of a rollout (measurement only).  `prof` records
+ * cudaEvents on the rollout's stream around the 4 kernels of every step; it
+ * never synchronises inside dgppo_rollout.  dgppo_prof_read waits for the last
+ * event and returns, per kernel kind [policy, step, lidar, graph], the summed
+ * (and optionally the maximum) device time in ms over the T steps of the most
+ * recent rollout that used it.                                               */
+void* dgppo_prof_create(int32_t T);
+void  dgppo_prof_destroy(void* prof);
+int   dgppo_prof_read(void* prof, float* ms_sum4, float* ms_max4 /* nullable */);
 
 #ifdef __cplusplus
 }

@@ -114,7 +114,7 @@ def test_rollout_per_step_parity(name, stochastic):
                                    p(rnn), p(e_d), p(actions), p(log_pis) if stochastic else None, p(rewards),
                                    p(costs), p(agent_ws), p(hits_ws), p(goal_d), p(obst), p(rays_d))
     cc = util.c_cfg(cfg)
-    rc = _lib.lib().dgppo_rollout(stream(), C.byref(cc), C.byref(nc), p(packed), C.byref(buf), T, b)
+    rc = _lib.lib().dgppo_rollout(stream(), C.byref(cc), C.byref(nc), p(packed), C.byref(buf), T, b, None)
     assert rc == 0
     torch.cuda.synchronize()
     R = {k: v.cpu().numpy() for k, v in rec.items()}
