@@ -228,10 +228,11 @@ class DGPPO(Algorithm):
         rnn_rec[:, T] = final_carry
         nc = self._env.n_cost
         Vh = torch.empty((b, T + 1, n, nc), dtype=torch.float32, device=nodes.device)
+        scratch = torch.empty_like(rnn_rec)     # rnn_out: the kernels' scratch rows (new carry is unused for Vh)
         cfg = self._env.env_cfg()
         _lib.check(_lib.lib().dgppo_gnn_value(
             stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
-            ptr(nodes), ptr(edges), ptr(recv), ptr(send), T + 1, ptr(rnn_rec), None, T + 1,
+            ptr(nodes), ptr(edges), ptr(recv), ptr(send), T + 1, ptr(rnn_rec), ptr(scratch), T + 1,
             ptr(Vh), T + 1, T + 1, b), "dgppo_gnn_value")
         return Vh
 
@@ -243,12 +244,13 @@ class DGPPO(Algorithm):
         b = g.nodes.shape[0]
         rnn_in = rnn_state.reshape(b, n, RNN_DIM).contiguous().float()
         Vh = torch.empty((b, n, self._env.n_cost), dtype=torch.float32, device=rnn_in.device)
+        scratch = torch.empty_like(rnn_in)
         cfg = self._env.env_cfg()
         nodes, edges = g.nodes.contiguous(), g.edges.contiguous()
         recv, send = g.receivers.contiguous(), g.senders.contiguous()
         _lib.check(_lib.lib().dgppo_gnn_value(
             stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
-            ptr(nodes), ptr(edges), ptr(recv), ptr(send), 1, ptr(rnn_in), None, 1, ptr(Vh), 1, 1, b),
+            ptr(nodes), ptr(edges), ptr(recv), ptr(send), 1, ptr(rnn_in), ptr(scratch), 1, ptr(Vh), 1, 1, b),
             "dgppo_gnn_value")
         return Vh[0] if single else Vh
 

@@ -14,39 +14,11 @@
 // which needs no per-sender key/value projection at all: ~6x fewer FLOPs at
 // LidarSpread n=8 and no (E, 3, d) intermediates.  Masked edges (recv = pad)
 // only feed the pad node, whose output no agent row ever reads.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "gnn_common.cuh"
 
 namespace dgppo {
-
-constexpr int R = 64;            // agent rows per tile
-constexpr int RS = 68;           // row stride of transposed buffers (floats)
-constexpr int NT = 256;          // threads per CTA
-constexpr int H = 3;             // attention heads
-constexpr int HID = 64;          // head / GRU width
-constexpr int X0S = 8;           // node-major stride of input node features
-constexpr int X1S = 36;          // node-major stride of layer-1 outputs (32 + pad)
-
-struct LayerP { const float *wq, *bq, *wkt, *wagg, *wu, *bu; int in, d; };
-
-struct NetP {
-  LayerP L[2];
-  int n_layers, kind, n_out;
-  const float *d0w, *d0b, *ln0s, *ln0b, *d1w, *d1b, *ln1s, *ln1b;
-  const float *wi, *bi, *wh, *bhn, *scale_w, *scale_b, *out_w, *out_b;
-};
-
-struct GnnArgs {
-  const float* nodes; const float* edges; const int* recv; const int* send;
-  int pitch, n_slots;
-  const float* rnn_in; float* rnn_out; int rnn_pitch;
-  const float* eps; int eps_pitch;
-  float* action; float* log_pi; int act_pitch;
-  float* value; int out_pitch;
-  int n_graphs;                 // b * n_slots
-  int n, N, E, nd, n_ag, n_ao, G;
-};
-
-__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
 // ---------------------------------------------------------------- tile GEMM
 // acc[i][j] (row r0+i, col c0+j) = scale1 * sum_k A1[k][r] W1(k)[c] + sum_k A2[k][r] W2(k)[c]
@@ -112,38 +84,6 @@ struct StoreT {
     }
   }
 };
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
-
-// tfp special_math.log_ndtr, float32 segments (lower -10, upper 5, 3-term series)
-__device__ __forceinline__ float ndtrf_(float x) {
-  const float hs2 = 0.70710678118654752440f;
-  const float w = x * hs2, z = fabsf(w);
-  const float y = (z < hs2) ? 1.f + erff(w) : ((w > 0.f) ? 2.f - erfcf(z) : erfcf(z));
-  return 0.5f * y;
-}
-__device__ __forceinline__ float log_ndtrf_(float x) {
-  if (x > 5.f) return -ndtrf_(-x);
-  if (x > -10.f) return logf(ndtrf_(fmaxf(x, -10.f)));
-  const float xl = fminf(x, -10.f), x2 = xl * xl;
-  const float series = 1.f - 1.f / x2 + 3.f / (x2 * x2) - 15.f / (x2 * x2 * x2);
-  return -0.5f * x2 - logf(-xl) - 0.91893853320467274178f + logf(series);
-}
-// TanhTransformedDistribution.log_prob for one action component
-__device__ __forceinline__ float tanh_normal_logp(float value, float loc, float scale) {
-  const float thr = 0.999f;
-  const float inv_thr = atanhf(thr);
-  const float log_eps = (float)-6.907755278982136;        // np.log(1.0 - 0.999)
-  const float v = fminf(fmaxf(value, -thr), thr);
-  if (v <= -thr) return log_ndtrf_((-inv_thr - loc) / scale) - log_eps;
-  if (v >= thr) return log_ndtrf_(-((inv_thr - loc) / scale)) - log_eps;
-  const float x = atanhf(v);
-  const float fldj = 2.f * (0.69314718055994530942f - x - softplusf_(-2.f * x));
-  const float d = x / scale - loc / scale;
-  const float lp = -0.5f * d * d - (0.91893853320467274178f + logf(scale));
-  return lp - fldj;
-}
 
 // ------------------------------------------------------------ attention
 // One thread per (row, head): two passes over the row's static edge slots
@@ -500,20 +440,7 @@ gnn_forward_kernel(NetP net, GnnArgs g, int m_cap) {
       const int gi = tile0 + gl;
       const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
       if (net.kind == DGPPO_NET_POLICY) {
-        const float m0 = q[0 * RS + r], m1 = q[1 * RS + r];
-        const size_t ao = ((size_t)env * g.act_pitch + slot) * n + i;
-        if (g.eps) {
-          const float inv = -0.43275212956718856f;     // log(exp(0.5) - 1)  (policy.py:54-59)
-          const float s0 = softplusf_(q[2 * RS + r] + inv) + 1e-5f;
-          const float s1 = softplusf_(q[3 * RS + r] + inv) + 1e-5f;
-          const float* ep = g.eps + (((size_t)env * g.eps_pitch + slot) * n + i) * 2;
-          const float a0 = tanhf(fmaf(s0, __ldg(ep), m0));
-          const float a1 = tanhf(fmaf(s1, __ldg(ep + 1), m1));
-          g.action[ao * 2] = a0; g.action[ao * 2 + 1] = a1;
-          if (g.log_pi) g.log_pi[ao] = tanh_normal_logp(a0, m0, s0) + tanh_normal_logp(a1, m1, s1);
-        } else {
-          g.action[ao * 2] = tanhf(m0); g.action[ao * 2 + 1] = tanhf(m1);   // mode (distribution.py:45-46)
-        }
+        policy_tail(g, q[0 * RS + r], q[1 * RS + r], q[2 * RS + r], q[3 * RS + r], env, slot, i, n);
       } else {
         float* vo = g.value + (((size_t)env * g.out_pitch + slot) * nr + i) * net.n_out;
         for (int c = 0; c < net.n_out; ++c) vo[c] = q[c * RS + r];
@@ -581,14 +508,21 @@ static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* n
   P.scale_b = (L.scale_b >= 0) ? params + L.scale_b : nullptr;
   P.out_w = params + L.out_w; P.out_b = params + L.out_b;
 
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // v2 (weight-stationary pair of kernels) when the shape fits; v1 fused kernel otherwise
+  const char* force_v1 = getenv("DGPPO_FORCE_V1");
+  if (!(force_v1 && force_v1[0] == '1')) {
+    const int rc2 = launch_gnn_v2(stream, P, L, params, g, sms);
+    if (rc2 != DGPPO_V2_UNSUPPORTED) return rc2;
+  }
+
   const size_t x0_fl = (size_t)m_cap * X0S > (size_t)HID * RS ? (size_t)m_cap * X0S : (size_t)HID * RS;
   const size_t fl = x0_fl + (net->n_layers == 2 ? (size_t)m_cap * X1S : 0) +
                     (size_t)(32 + 192 + H * 36 + HID) * RS;
   const size_t smem = fl * sizeof(float);
   if (smem > 227 * 1024) return DGPPO_ENOTSUP;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
   const int grid = n_tiles < sms ? n_tiles : sms;
   cudaError_t err;

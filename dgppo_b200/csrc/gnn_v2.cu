@@ -1,0 +1,599 @@
+// K4 v2: weight-stationary GraphTransformer forward for sm_100a (FP32 FFMA).
+//
+// The v1 kernel (gnn_kernels.cu) streams every weight through L1/L2 inside the
+// GEMM k-loops and is latency-bound on those loads (profiles/r1_policy_v1.ncu.txt:
+// 40% long-scoreboard stalls, 15% FMA-pipe utilisation).  v2 splits the forward
+// into two persistent kernels whose weights are loaded ONCE per CTA into shared
+// memory and stay there for every tile:
+//
+//   gnn_layers_kernel : GNN layers for a tile of G graphs (G*n <= 32 agent rows);
+//                       smem = GNN weights (~99 KB) + node/row activations.
+//                       Output: agent embeddings (rows x 64) into the caller's
+//                       rnn_out buffer, used as scratch.
+//   head_kernel       : head MLP + LayerNorm + GRU + tails for a tile of 64 rows;
+//                       smem = head/GRU/tail weights (~148 KB) + activations.
+//                       Reads the embeddings back from rnn_out, then overwrites
+//                       them with the new GRU carry.
+//
+// Same arithmetic as v1 (GNN regrouping); attention is parallelised
+// over (row, head, edge slot) instead of (row, head).
+#include "gnn_common.cuh"
+
+namespace dgppo {
+
+constexpr int R2 = 32;           // agent rows per GNN tile
+constexpr int RS2 = 36;          // row stride of the GNN tile's transposed buffers
+constexpr int QTS = 36;          // per-(row, head) stride of the regrouped keys
+
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Register-tiled GEMM over a tile of ROWS rows: thread tile RT rows x 4 cols,
+// A operands transposed [k][row] (stride AS) in smem, W row-major [k][ld] in smem.
+// A warp covers 8 row groups x 4 col groups: one smem wavefront per operand load.
+// acc = scale1 * A1 W1 + A2 W2.
+template <int ROWS, int AS, int RT, class Epi>
+__device__ __forceinline__ void gemm_ws(const float* A1, int K1, const float* W1, int ld1, float scale1,
+                                        const float* A2, int K2, const float* W2, int ld2,
+                                        int N4, Epi epi) {
+  constexpr int NRG = ROWS / RT;             // row groups
+  constexpr int NRGB = NRG / 8;              // blocks of 8 row groups
+  const int ncgb = (N4 + 3) >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int bi = warp; bi < NRGB * ncgb; bi += NT / 32) {
+    const int rgb = bi % NRGB, cgb = bi / NRGB;
+    const int rg = rgb * 8 + (lane & 7), cg = cgb * 4 + (lane >> 3);
+    if (cg >= N4) continue;
+    float acc[RT][4];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    auto run = [&](const float* A, int K, const float* W, int ld) {
+      const float* ap = A + rg * RT;
+      const float* wp = W + cg * 4;
+#pragma unroll 8
+      for (int k = 0; k < K; ++k) {
+        float av[RT];
+        if constexpr (RT == 4) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + k * AS);
+          av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+        } else {
+          const float2 a = *reinterpret_cast<const float2*>(ap + k * AS);
+          av[0] = a.x; av[1] = a.y;
+        }
+        const float4 w = *reinterpret_cast<const float4*>(wp + (size_t)k * ld);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      }
+    };
+    run(A1, K1, W1, ld1);
+    if (K2 > 0) {
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] *= scale1;
+      run(A2, K2, W2, ld2);
+    }
+    epi(rg * RT, cg * 4, acc);
+  }
+}
+
+struct GnnV2Plan {
+  int w_off, w_fl;        // GNN weights: [w_off, w_off + w_fl) floats of the packed buffer
+  int m_cap, deg;
+  int x0_fl, x1_fl, sidx_fl, sc_fl;
+  size_t smem_bytes;
+  int hw_off, hw_fl;      // head weights
+  size_t head_smem_bytes;
+};
+
+// ------------------------------------------------------------ GNN layers
+template <int NL>
+__global__ void __launch_bounds__(NT, 1)
+gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;                                    // GNN weights
+  float* x0 = ws + pl.w_fl;                            // [M][8]
+  float* x1 = x0 + pl.x0_fl;                           // [M][36]
+  float* xr = x1 + pl.x1_fl;                           // [32][RS2]
+  float* q = xr + 32 * RS2;                            // [192][RS2]; z aliases it
+  float* qt = q + 192 * RS2;                           // [R2][H][QTS]
+  int* sidx = reinterpret_cast<int*>(qt + R2 * H * QTS);   // [R2][deg]
+  float* sc = reinterpret_cast<float*>(sidx) + pl.sidx_fl; // [R2][H][deg]
+  float* z = q;
+
+  for (int i = threadIdx.x; i < pl.w_fl / 4; i += NT) cp_async16(ws + 4 * i, params + pl.w_off + 4 * i);
+  cp_async_wait_all();
+  __syncthreads();
+  auto wptr = [&](const float* p) { return ws + ((p - params) - pl.w_off); };
+
+  const int n = g.n, N = g.N, nd = g.nd, G = g.G, deg = pl.deg;
+  const int nodes_per = N - 1, pad = N - 1;
+  const int n_tiles = (g.n_graphs + G - 1) / G;
+  const int nr_out = (net.kind == DGPPO_NET_VL) ? 1 : n;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tile0 = tile * G;
+    const int gcount = min(G, g.n_graphs - tile0);
+    const int rows = gcount * n;
+    const int M = gcount * nodes_per;
+    __syncthreads();
+
+    // ---- stage node features (async) and the per-row sender table
+    for (int idx = threadIdx.x; idx < M * X0S; idx += NT) {
+      const int s = idx / X0S, c = idx - s * X0S;
+      if (c < nd) {
+        const int gl = s / nodes_per, node = s - gl * nodes_per;
+        const int gi = tile0 + gl;
+        const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+        cp_async4(x0 + idx, g.nodes + ((size_t)env * g.pitch + slot) * N * nd + node * nd + c);
+      } else {
+        x0[idx] = 0.f;
+      }
+    }
+    for (int idx = threadIdx.x; idx < R2 * deg; idx += NT) {
+      const int r = idx / deg, t = idx - r * deg;
+      int s = -1;
+      if (r < rows) {
+        const int gl = r / n, i = r - gl * n;
+        const int gi = tile0 + gl;
+        const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+        const size_t gslot = (size_t)env * g.pitch + slot;
+        const int e = (t < n) ? i * n + t
+                              : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
+                                                  : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
+        if (__ldg(g.recv + gslot * g.E + e) != pad) s = gl * nodes_per + __ldg(g.send + gslot * g.E + e);
+      }
+      sidx[idx] = s;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const float* X = x0; int XS = X0S;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const LayerP& P = net.L[l];
+      const int IN = P.in, D = P.d, HD = H * D, INP = round4(IN + 1), INA = IN + 5;
+      const bool last = (l == NL - 1);
+      const int INX = (l == 0) ? X0S : 32;             // feature columns staged per node
+      const float *wq = wptr(P.wq), *bq = wptr(P.bq), *wkt = wptr(P.wkt), *wagg = wptr(P.wagg),
+                  *wu = wptr(P.wu), *bu = wptr(P.bu);
+
+      for (int idx = threadIdx.x; idx < 32 * R2; idx += NT) {       // xr[c][r] = X[node(r)][c]
+        const int c = idx / R2, r = idx - c * R2;
+        float v = 0.f;
+        if (r < rows && c < IN) { const int gl = r / n, i = r - gl * n; v = X[((size_t)gl * nodes_per + i) * XS + c]; }
+        xr[c * RS2 + r] = v;
+      }
+      __syncthreads();
+      // q = xr Wq + bq  -> q[c][r]
+      gemm_ws<R2, RS2, 4>(xr, IN, wq, HD, 1.f, nullptr, 0, nullptr, 0, HD / 4,
+                          [&](int r0, int c0, float (&acc)[4][4]) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                              const float bj = bq[c0 + j];
+                              *reinterpret_cast<float4*>(q + (c0 + j) * RS2 + r0) =
+                                  make_float4(acc[0][j] + bj, acc[1][j] + bj, acc[2][j] + bj, acc[3][j] + bj);
+                            }
+                          });
+      __syncthreads();
+      // qt[r][h][:] = Wk_h^T q_h[r]  (column IN carries q_h . bk_h)
+      for (int h = 0; h < H; ++h)
+        gemm_ws<R2, RS2, 2>(q + (h * D) * RS2, D, wkt + (size_t)h * D * INP, INP, 1.f, nullptr, 0, nullptr, 0,
+                            INP / 4, [&](int r0, int c0, float (&acc)[2][4]) {
+#pragma unroll
+                              for (int i = 0; i < 2; ++i)
+                                *reinterpret_cast<float4*>(qt + ((r0 + i) * H + h) * QTS + c0) =
+                                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                            });
+      __syncthreads();
+      // ---- attention phase A: scores per (row, head, slot)
+      const float isd = 1.f / sqrtf((float)D);
+      for (int idx = threadIdx.x; idx < R2 * H * deg; idx += NT) {
+        const int t = idx % deg, rh = idx / deg, r = rh / H;
+        const int s = sidx[r * deg + t];
+        float v = -INFINITY;
+        if (s >= 0) {
+          const float* qp = qt + rh * QTS;
+          const float* xp = X + (size_t)s * XS;
+          float acc = qp[IN];
+          for (int c = 0; c < INX; c += 4) {
+            const float4 qv = *reinterpret_cast<const float4*>(qp + c);
+            const float4 xv = *reinterpret_cast<const float4*>(xp + c);
+            if (c < IN) acc = fmaf(qv.x, xv.x, acc);
+            if (c + 1 < IN) acc = fmaf(qv.y, xv.y, acc);
+            if (c + 2 < IN) acc = fmaf(qv.z, xv.z, acc);
+            if (c + 3 < IN) acc = fmaf(qv.w, xv.w, acc);
+          }
+          v = acc * isd;
+        }
+        sc[idx] = v;
+      }
+      __syncthreads();
+      // ---- phase B: softmax over the row's slots (jraph.segment_softmax; gnn.py:101)
+      for (int rh = threadIdx.x; rh < R2 * H; rh += NT) {
+        float* sp = sc + rh * deg;
+        float mx = -INFINITY;
+        for (int t = 0; t < deg; ++t) mx = fmaxf(mx, sp[t]);
+        float l = 0.f;
+        if (mx > -INFINITY) {
+          for (int t = 0; t < deg; ++t) { const float p = expf(sp[t] - mx); sp[t] = p; l += p; }
+          const float inv_l = 1.f / l;
+          for (int t = 0; t < deg; ++t) sp[t] *= inv_l;
+        } else {
+          for (int t = 0; t < deg; ++t) sp[t] = 0.f;
+        }
+        const int r = rh / H, h = rh - r * H;
+        z[(h * INA + IN) * RS2 + r] = (l > 0.f) ? 1.f : 0.f;
+      }
+      __syncthreads();
+      // ---- phase C: weighted sums of sender features / edge features
+      const int ngrp = INX / 4 + 1;
+      for (int idx = threadIdx.x; idx < R2 * H * ngrp; idx += NT) {
+        const int grp = idx % ngrp, rh = idx / ngrp, r = rh / H, h = rh - r * H;
+        const float* sp = sc + rh * deg;
+        const int* si = sidx + r * deg;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (grp < ngrp - 1) {
+          for (int t = 0; t < deg; ++t) {
+            const float a = sp[t];
+            if (a == 0.f) continue;
+            const float4 xv = *reinterpret_cast<const float4*>(X + (size_t)si[t] * XS + grp * 4);
+            a0 = fmaf(a, xv.x, a0); a1 = fmaf(a, xv.y, a1); a2 = fmaf(a, xv.z, a2); a3 = fmaf(a, xv.w, a3);
+          }
+          const int c = grp * 4;
+          float* zc = z + (h * INA + c) * RS2 + r;
+          zc[0] = a0;
+          if (c + 1 < IN) zc[RS2] = a1;
+          if (c + 2 < IN) zc[2 * RS2] = a2;
+          if (c + 3 < IN) zc[3 * RS2] = a3;
+        } else {
+          if (r < rows) {
+            const int gl = r / n, i = r - gl * n;
+            const int gi = tile0 + gl;
+            const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+            const float4* ed = reinterpret_cast<const float4*>(g.edges + ((size_t)env * g.pitch + slot) * g.E * 4);
+            for (int t = 0; t < deg; ++t) {
+              const float a = sp[t];
+              if (a == 0.f) continue;
+              const int e = (t < n) ? i * n + t
+                                    : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
+                                                        : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
+              const float4 ef = __ldg(ed + e);
+              a0 = fmaf(a, ef.x, a0); a1 = fmaf(a, ef.y, a1); a2 = fmaf(a, ef.z, a2); a3 = fmaf(a, ef.w, a3);
+            }
+          }
+          float* zc = z + (h * INA + IN + 1) * RS2 + r;
+          zc[0] = a0; zc[RS2] = a1; zc[2 * RS2] = a2; zc[3 * RS2] = a3;
+        }
+      }
+      __syncthreads();
+      // ---- x' = relu(x Wu + bu + 1/H z Wagg)
+      if (!last) {
+        gemm_ws<R2, RS2, 2>(z, H * INA, wagg, D, 1.f / H, xr, IN, wu, D, D / 4,
+                            [&](int r0, int c0, float (&acc)[2][4]) {
+#pragma unroll
+                              for (int i = 0; i < 2; ++i) {
+                                const int r = r0 + i;
+                                if (r < rows) {
+                                  const int gl = r / n, ia = r - gl * n;
+                                  float* dst = x1 + ((size_t)gl * nodes_per + ia) * X1S + c0;
+                                  *reinterpret_cast<float4*>(dst) =
+                                      make_float4(fmaxf(acc[i][0] + bu[c0], 0.f), fmaxf(acc[i][1] + bu[c0 + 1], 0.f),
+                                                  fmaxf(acc[i][2] + bu[c0 + 2], 0.f), fmaxf(acc[i][3] + bu[c0 + 3], 0.f));
+                                }
+                              }
+                            });
+        for (int idx = threadIdx.x; idx < M * 8; idx += NT) {           // non-agent nodes
+          const int s = idx >> 3, c0 = (idx & 7) * 4;
+          const int node = s % nodes_per;
+          if (node < n) continue;
+          const float* x = X + (size_t)s * XS;
+          float a0 = bu[c0], a1 = bu[c0 + 1], a2 = bu[c0 + 2], a3 = bu[c0 + 3];
+          for (int c = 0; c < IN; ++c) {
+            const float xv = x[c];
+            const float4 w = *reinterpret_cast<const float4*>(wu + c * D + c0);
+            a0 = fmaf(xv, w.x, a0); a1 = fmaf(xv, w.y, a1); a2 = fmaf(xv, w.z, a2); a3 = fmaf(xv, w.w, a3);
+          }
+          *reinterpret_cast<float4*>(x1 + (size_t)s * X1S + c0) =
+              make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+        }
+        X = x1; XS = X1S;
+      } else if (net.kind != DGPPO_NET_VL) {
+        // final embeddings straight to the scratch rows (rnn_out layout)
+        gemm_ws<R2, RS2, 2>(z, H * INA, wagg, D, 1.f / H, xr, IN, wu, D, D / 4,
+                            [&](int r0, int c0, float (&acc)[2][4]) {
+#pragma unroll
+                              for (int i = 0; i < 2; ++i) {
+                                const int r = r0 + i;
+                                if (r < rows) {
+                                  const int gl = r / n, ia = r - gl * n;
+                                  const int gi = tile0 + gl;
+                                  const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+                                  float* dst = g.rnn_out + (((size_t)env * g.rnn_pitch + slot) * n + ia) * HID + c0;
+                                  *reinterpret_cast<float4*>(dst) =
+                                      make_float4(fmaxf(acc[i][0] + bu[c0], 0.f), fmaxf(acc[i][1] + bu[c0 + 1], 0.f),
+                                                  fmaxf(acc[i][2] + bu[c0 + 2], 0.f), fmaxf(acc[i][3] + bu[c0 + 3], 0.f));
+                                }
+                              }
+                            });
+      } else {
+        // centralised Vl: mean over the agents of each graph (value.py:28-31)
+        float* ob = x0;                                    // [64][RS2]; x0 is dead by now
+        gemm_ws<R2, RS2, 2>(z, H * INA, wagg, D, 1.f / H, xr, IN, wu, D, D / 4,
+                            [&](int r0, int c0, float (&acc)[2][4]) {
+#pragma unroll
+                              for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float2*>(ob + (c0 + j) * RS2 + r0) =
+                                    make_float2(fmaxf(acc[0][j] + bu[c0 + j], 0.f), fmaxf(acc[1][j] + bu[c0 + j], 0.f));
+                            });
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < HID * gcount; idx += NT) {
+          const int gl = idx / HID, c = idx - gl * HID;
+          float sacc = 0.f;
+          for (int i = 0; i < n; ++i) sacc += ob[c * RS2 + gl * n + i];
+          const int gi = tile0 + gl;
+          const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+          g.rnn_out[(((size_t)env * g.rnn_pitch + slot) * nr_out) * HID + c] = sacc / (float)n;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ head
+// Each WARP owns 8 rows of the tile end to end (head MLP -> LayerNorm -> GRU ->
+// tails); lanes span the output columns {lane, lane + 32}.  The A operand (the
+// warp's 8 rows of one feature) is a warp-uniform 2 x LDS.128, the weight row a
+// conflict-free LDS.32 per column: 4-6 FFMA per shared-memory wavefront, and no
+// block-wide barrier inside the tile loop (warps never exchange data).
+constexpr int WR = 8;            // rows per warp
+
+// out[c][r0..r0+7] = bias[c] + sum_k A[k][r0..r0+7] * W[k][c]   for c = lane, lane + 32
+__device__ __forceinline__ void warp_dense64(const float* A, const float* W, const float* bias,
+                                             float* out, int r0, int lane) {
+  float acc[WR][2];
+#pragma unroll
+  for (int i = 0; i < WR; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+#pragma unroll 4
+  for (int k = 0; k < HID; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(A + k * RS + r0);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + k * RS + r0 + 4);
+    const float w0 = W[k * HID + lane], w1 = W[k * HID + lane + 32];
+    const float av[WR] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < WR; ++i) { acc[i][0] = fmaf(av[i], w0, acc[i][0]); acc[i][1] = fmaf(av[i], w1, acc[i][1]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = lane + 32 * j;
+    const float bj = bias[c];
+    *reinterpret_cast<float4*>(out + c * RS + r0) =
+        make_float4(acc[0][j] + bj, acc[1][j] + bj, acc[2][j] + bj, acc[3][j] + bj);
+    *reinterpret_cast<float4*>(out + c * RS + r0 + 4) =
+        make_float4(acc[4][j] + bj, acc[5][j] + bj, acc[6][j] + bj, acc[7][j] + bj);
+  }
+}
+
+// LayerNorm (flax: eps 1e-6, fast variance) + ReLU over the 64 features of the
+// warp's 8 rows; 4 lanes per row, features interleaved.
+__device__ __forceinline__ void warp_layernorm_relu(float* y, const float* scale, const float* bias,
+                                                    int r0, int lane) {
+  const int r = r0 + (lane >> 2), part = lane & 3;
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < HID / 4; ++i) { const float v = y[(i * 4 + part) * RS + r]; s += v; s2 = fmaf(v, v, s2); }
+  s += __shfl_xor_sync(0xffffffffu, s, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  const float mean = s * (1.f / HID), mean2 = s2 * (1.f / HID);
+  const float var = fmaxf(0.f, mean2 - mean * mean);
+  const float rstd = 1.f / sqrtf(var + 1e-6f);
+#pragma unroll
+  for (int i = 0; i < HID / 4; ++i) {
+    const int c = i * 4 + part;
+    y[c * RS + r] = fmaxf((y[c * RS + r] - mean) * (rstd * scale[c]) + bias[c], 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;                                   // head / GRU / tail weights
+  float* y0 = ws + pl.hw_fl;                          // [64][RS]
+  float* y1 = y0 + HID * RS;
+  float* hbuf = y1 + HID * RS;
+  float* o4 = hbuf + HID * RS;                        // [4][RS]
+  for (int i = threadIdx.x; i < pl.hw_fl / 4; i += NT) cp_async16(ws + 4 * i, params + pl.hw_off + 4 * i);
+  cp_async_wait_all();
+  __syncthreads();
+  auto wptr = [&](const float* p) { return ws + ((p - params) - pl.hw_off); };
+  const float *d0w = wptr(net.d0w), *d0b = wptr(net.d0b), *ln0s = wptr(net.ln0s), *ln0b = wptr(net.ln0b);
+  const float *d1w = wptr(net.d1w), *d1b = wptr(net.d1b), *ln1s = wptr(net.ln1s), *ln1b = wptr(net.ln1b);
+  const float *wi = wptr(net.wi), *bi = wptr(net.bi), *wh = wptr(net.wh), *bhn = wptr(net.bhn);
+  const float *out_w = wptr(net.out_w), *out_b = wptr(net.out_b);
+  const bool policy = net.kind == DGPPO_NET_POLICY;
+  const float *scale_w = policy ? wptr(net.scale_w) : nullptr, *scale_b = policy ? wptr(net.scale_b) : nullptr;
+
+  const int n = g.n;
+  const int nr = (net.kind == DGPPO_NET_VL) ? 1 : n;       // rows per graph
+  const long total_rows = (long)g.n_graphs * nr;
+  const long n_wtiles = (total_rows + WR - 1) / WR;         // 8-row warp tiles
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = warp * WR;                                 // the warp's rows inside the CTA buffers
+  // row -> flat offset of its 64-float record in rnn_in / rnn_out
+  auto row_off = [&](long row) {
+    const long gi = row / nr; const int i = (int)(row - gi * nr);
+    const long env = gi / g.n_slots; const int slot = (int)(gi - env * g.n_slots);
+    return (((size_t)env * g.rnn_pitch + slot) * nr + i) * HID;
+  };
+
+  for (long wt = (long)blockIdx.x * (NT / 32) + warp; wt < n_wtiles; wt += (long)gridDim.x * (NT / 32)) {
+    const long row0 = wt * WR;
+    const int rows = (int)min((long)WR, total_rows - row0);
+    __syncwarp();
+    // embeddings (scratch rows in rnn_out) -> y0, previous carry -> hbuf, transposed
+    for (int i = 0; i < WR; ++i) {
+      if (i < rows) {
+        const size_t off = row_off(row0 + i);
+        cp_async4(y0 + lane * RS + r0 + i, g.rnn_out + off + lane);
+        cp_async4(y0 + (lane + 32) * RS + r0 + i, g.rnn_out + off + lane + 32);
+        cp_async4(hbuf + lane * RS + r0 + i, g.rnn_in + off + lane);
+        cp_async4(hbuf + (lane + 32) * RS + r0 + i, g.rnn_in + off + lane + 32);
+      } else {
+        y0[lane * RS + r0 + i] = 0.f; y0[(lane + 32) * RS + r0 + i] = 0.f;
+        hbuf[lane * RS + r0 + i] = 0.f; hbuf[(lane + 32) * RS + r0 + i] = 0.f;
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // head MLP: 2 x [Dense64 -> LayerNorm -> ReLU]   (mlp.py:14-30)
+    warp_dense64(y0, d0w, d0b, y1, r0, lane);
+    __syncwarp();
+    warp_layernorm_relu(y1, ln0s, ln0b, r0, lane);
+    __syncwarp();
+    warp_dense64(y1, d1w, d1b, y0, r0, lane);
+    __syncwarp();
+    warp_layernorm_relu(y0, ln1s, ln1b, r0, lane);
+    __syncwarp();
+    // GRU cell (flax GRUCell; rnn.py:19-21): 8 rows x units {lane, lane+32} x 3 gates
+    {
+      float ai[3][WR][2], ah[3][WR][2];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int i = 0; i < WR; ++i) { ai[t][i][0] = ai[t][i][1] = 0.f; ah[t][i][0] = ah[t][i][1] = 0.f; }
+#pragma unroll 2
+      for (int k = 0; k < HID; ++k) {
+        const float4 x0v = *reinterpret_cast<const float4*>(y0 + k * RS + r0);
+        const float4 x1v = *reinterpret_cast<const float4*>(y0 + k * RS + r0 + 4);
+        const float4 h0v = *reinterpret_cast<const float4*>(hbuf + k * RS + r0);
+        const float4 h1v = *reinterpret_cast<const float4*>(hbuf + k * RS + r0 + 4);
+        const float xv[WR] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
+        const float hv[WR] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const float wi0 = wi[k * 192 + t * 64 + lane], wi1 = wi[k * 192 + t * 64 + lane + 32];
+          const float wh0 = wh[k * 192 + t * 64 + lane], wh1 = wh[k * 192 + t * 64 + lane + 32];
+#pragma unroll
+          for (int i = 0; i < WR; ++i) {
+            ai[t][i][0] = fmaf(xv[i], wi0, ai[t][i][0]); ai[t][i][1] = fmaf(xv[i], wi1, ai[t][i][1]);
+            ah[t][i][0] = fmaf(hv[i], wh0, ah[t][i][0]); ah[t][i][1] = fmaf(hv[i], wh1, ah[t][i][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = lane + 32 * j;
+        const float bir = bi[c], biz = bi[64 + c], bin = bi[128 + c], bh = bhn[c];
+        float hn[WR];
+#pragma unroll
+        for (int i = 0; i < WR; ++i) {
+          const float hprev = hbuf[c * RS + r0 + i];
+          const float rgate = sigmoidf_(ai[0][i][j] + bir + ah[0][i][j]);
+          const float zgate = sigmoidf_(ai[1][i][j] + biz + ah[1][i][j]);
+          const float cand = tanhf(ai[2][i][j] + bin + rgate * (ah[2][i][j] + bh));
+          hn[i] = (1.f - zgate) * cand + zgate * hprev;
+        }
+        *reinterpret_cast<float4*>(y1 + c * RS + r0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(y1 + c * RS + r0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        // new carry -> rnn_out (overwrites the scratch embeddings); coalesced across lanes
+#pragma unroll
+        for (int i = 0; i < WR; ++i)
+          if (i < rows) g.rnn_out[row_off(row0 + i) + c] = hn[i];
+      }
+    }
+    __syncwarp();
+    const float* feat = y1;
+    if (policy) {
+      warp_dense64(y1, scale_w, scale_b, y0, r0, lane);       // ScaleHid (policy.py:67)
+      __syncwarp();
+      feat = y0;
+    }
+    {   // out: [64] -> 4 columns; lane = (row, column)
+      const int rr = lane >> 2, col = lane & 3;
+      float acc = out_b[col];
+#pragma unroll 8
+      for (int k = 0; k < HID; ++k) acc = fmaf(feat[k * RS + r0 + rr], out_w[k * 4 + col], acc);
+      o4[col * RS + r0 + rr] = acc;
+    }
+    __syncwarp();
+    if (lane < rows) {
+      const int r = r0 + lane;
+      const long row = row0 + lane;
+      const long gi = row / nr; const int i = (int)(row - gi * nr);
+      const long env = gi / g.n_slots; const int slot = (int)(gi - env * g.n_slots);
+      if (policy) {
+        policy_tail(g, o4[r], o4[RS + r], o4[2 * RS + r], o4[3 * RS + r], (int)env, slot, i, n);
+      } else {
+        float* vo = g.value + ((((size_t)env * g.out_pitch + slot) * nr + i) * net.n_out);
+        for (int c = 0; c < net.n_out; ++c) vo[c] = o4[c * RS + r];
+      }
+    }
+  }
+}
+
+int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const float* params,
+                  const GnnArgs& g_in, int sms) {
+  if (!g_in.rnn_out || g_in.rnn_out == g_in.rnn_in) return DGPPO_V2_UNSUPPORTED;
+  if (g_in.n > R2) return DGPPO_V2_UNSUPPORTED;
+  GnnArgs g = g_in;
+  g.G = R2 / g.n;
+  GnnV2Plan pl;
+  pl.w_off = L.wq[0];
+  pl.w_fl = L.d0w - L.wq[0];
+  pl.hw_off = L.d0w;
+  pl.hw_fl = L.total - L.d0w;
+  pl.m_cap = g.G * (g.N - 1);
+  pl.deg = g.n + g.n_ag + g.n_ao;
+  pl.x0_fl = pl.m_cap * X0S;
+  if (P.kind == DGPPO_NET_VL && pl.x0_fl < HID * RS2) pl.x0_fl = HID * RS2;
+  pl.x1_fl = (P.n_layers == 2) ? pl.m_cap * X1S : 0;
+  pl.sidx_fl = round4(R2 * pl.deg);
+  pl.sc_fl = round4(R2 * H * pl.deg);
+  const size_t fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + 192 * RS2 + R2 * H * QTS +
+                    pl.sidx_fl + pl.sc_fl;
+  pl.smem_bytes = fl * sizeof(float);
+  pl.head_smem_bytes = ((size_t)pl.hw_fl + 3 * HID * RS + 4 * RS) * sizeof(float);
+  if (pl.smem_bytes > 227 * 1024 || pl.head_smem_bytes > 227 * 1024) return DGPPO_V2_UNSUPPORTED;
+  if ((pl.w_off & 3) || (pl.w_fl & 3) || (pl.hw_fl & 3)) return DGPPO_V2_UNSUPPORTED;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
+  const int grid1 = n_tiles < sms ? n_tiles : sms;
+  cudaError_t err;
+  if (P.n_layers == 2) {
+    err = cudaFuncSetAttribute(gnn_layers_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (err != cudaSuccess) return (int)err;
+    gnn_layers_kernel<2><<<grid1, NT, pl.smem_bytes, st>>>(P, g, pl, params);
+  } else {
+    err = cudaFuncSetAttribute(gnn_layers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (err != cudaSuccess) return (int)err;
+    gnn_layers_kernel<1><<<grid1, NT, pl.smem_bytes, st>>>(P, g, pl, params);
+  }
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return (int)err;
+  const int nr = (P.kind == DGPPO_NET_VL) ? 1 : g.n;
+  const long total_rows = (long)g.n_graphs * nr;
+  const long h_tiles = (total_rows + R - 1) / R;             // CTAs worth of 8-row warp tiles
+  const int grid2 = h_tiles < sms ? (int)h_tiles : sms;
+  err = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.head_smem_bytes);
+  if (err != cudaSuccess) return (int)err;
+  head_kernel<<<grid2, NT, pl.head_smem_bytes, st>>>(P, g, pl, params);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dgppo

@@ -16,6 +16,14 @@ F = np.float32
 RTOL, ATOL = 1e-5, 1e-5
 
 
+@pytest.fixture(params=["v2", "v1"], autouse=True)
+def kernel_generation(request, monkeypatch):
+    """Every test runs on the weight-stationary v2 kernels (default when the
+    shape fits) and on the fused v1 kernel (DGPPO_FORCE_V1=1, the large-n path)."""
+    monkeypatch.setenv("DGPPO_FORCE_V1", "1" if request.param == "v1" else "0")
+    return request.param
+
+
 def _graph(cfg, b, seed):
     agent, goal, obstacles, mpe_obs = util.threshold_states(cfg, b, seed)
     return env_np.reset_graph(cfg, agent, goal, obstacles, mpe_obs)
