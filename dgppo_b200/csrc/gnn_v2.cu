@@ -39,17 +39,19 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // Register-tiled GEMM over a tile of ROWS rows: thread tile RT rows x 4 cols,
 // A operands transposed [k][row] (stride AS) in smem, W row-major [k][ld] in smem.
-// A warp covers 8 row groups x 4 col groups: one smem wavefront per operand load.
-// acc = scale1 * A1 W1 + A2 W2.
+// A warp covers 8 row groups x 4 col groups.  Warps [w0, w0 + nw) of the CTA take
+// part; the reduction runs over k in [k_lo, k_hi) of source 1 (+ all of source 2
+// when K2 > 0):  acc = scale1 * A1 W1 + A2 W2.
 template <int ROWS, int AS, int RT, class Epi>
-__device__ __forceinline__ void gemm_ws(const float* A1, int K1, const float* W1, int ld1, float scale1,
+__device__ __forceinline__ void gemm_ws(const float* A1, int k_lo, int k_hi, const float* W1, int ld1, float scale1,
                                         const float* A2, int K2, const float* W2, int ld2,
-                                        int N4, Epi epi) {
+                                        int N4, int w0, int nw, Epi epi) {
   constexpr int NRG = ROWS / RT;             // row groups
   constexpr int NRGB = NRG / 8;              // blocks of 8 row groups
   const int ncgb = (N4 + 3) >> 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int bi = warp; bi < NRGB * ncgb; bi += NT / 32) {
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) - w0;
+  if (warp < 0 || warp >= nw) return;
+  for (int bi = warp; bi < NRGB * ncgb; bi += nw) {
     const int rgb = bi % NRGB, cgb = bi / NRGB;
     const int rg = rgb * 8 + (lane & 7), cg = cgb * 4 + (lane >> 3);
     if (cg >= N4) continue;
@@ -58,11 +60,11 @@ __device__ __forceinline__ void gemm_ws(const float* A1, int K1, const float* W1
     for (int i = 0; i < RT; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    auto run = [&](const float* A, int K, const float* W, int ld) {
+    auto run = [&](const float* A, int ka, int kb, const float* W, int ld) {
       const float* ap = A + rg * RT;
       const float* wp = W + cg * 4;
 #pragma unroll 8
-      for (int k = 0; k < K; ++k) {
+      for (int k = ka; k < kb; ++k) {
         float av[RT];
         if constexpr (RT == 4) {
           const float4 a = *reinterpret_cast<const float4*>(ap + k * AS);
@@ -79,79 +81,200 @@ __device__ __forceinline__ void gemm_ws(const float* A1, int K1, const float* W1
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
       }
     };
-    run(A1, K1, W1, ld1);
-    if (K2 > 0) {
+    run(A1, k_lo, k_hi, W1, ld1);
+    if (scale1 != 1.f) {
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] *= scale1;
-      run(A2, K2, W2, ld2);
     }
+    if (K2 > 0) run(A2, 0, K2, W2, ld2);
     epi(rg * RT, cg * 4, acc);
   }
 }
 
 struct GnnV2Plan {
   int w_off, w_fl;        // GNN weights: [w_off, w_off + w_fl) floats of the packed buffer
-  int m_cap, deg;
-  int x0_fl, x1_fl, sidx_fl, sc_fl;
+  int m_cap, deg, degp;   // degp: slots per row padded to a multiple of 32
+  int x0_fl, x1_fl, sidx_fl, scr_fl;
+  int threads;            // CTA size of gnn_layers_kernel (512 or 256)
   size_t smem_bytes;
   int hw_off, hw_fl;      // head weights
   size_t head_smem_bytes;
 };
 
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Attention of ONE receiver row by ONE warp (gnn.py:100-107,114 regrouped):
+//   lane t scores slot t for the 3 heads -> warp softmax -> weights staged in the
+//   warp's scratch -> lanes turn into feature columns and accumulate the weighted
+//   sender features; 12 lanes accumulate the weighted edge features.
+// Writes column r of z[(h*INA + c)][r].
+template <int INX, int J>
+__device__ __forceinline__ void attention_row(int r, bool live, int lane, const int* srow, int deg,
+                                              const float* qrow /* qt + r*H*QTS */, int IN, float isd,
+                                              const float* X, int XS, const float4* ed, int i_agent,
+                                              int n, int n_ag, int n_ao, float* scr, float* z) {
+  const int INA = IN + 5;
+  float* zc = z + r;
+  if (!live) {                                   // rows past the tile's graphs: zero column
+    for (int c = lane; c < H * INA; c += 32) zc[c * RS2] = 0.f;
+    return;
+  }
+  float* at = scr;                               // [degp][4]: a_h[t], h < 3
+  float* eft = scr + J * 32 * 4;                 // [degp][4]: edge features of slot t
+  int sv[J];
+  float sc[J][H];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int t = lane + 32 * j;
+    sv[j] = (t < deg) ? srow[t] : -1;
+#pragma unroll
+    for (int h = 0; h < H; ++h) sc[j][h] = -INFINITY;
+    float4 ef = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sv[j] >= 0) {
+      const float* xp = X + (size_t)sv[j] * XS;
+      float acc[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) acc[h] = qrow[h * QTS + IN];
+#pragma unroll
+      for (int c = 0; c < INX; c += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + c);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float4 qv = *reinterpret_cast<const float4*>(qrow + h * QTS + c);
+          acc[h] = fmaf(qv.x, xv.x, acc[h]); acc[h] = fmaf(qv.y, xv.y, acc[h]);
+          acc[h] = fmaf(qv.z, xv.z, acc[h]); acc[h] = fmaf(qv.w, xv.w, acc[h]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) sc[j][h] = acc[h] * isd;
+      const int e = (t < n) ? i_agent * n + t
+                            : ((t < n + n_ag) ? n * n + i_agent * n_ag + (t - n)
+                                              : n * n + n * n_ag + i_agent * n_ao + (t - n - n_ag));
+      ef = __ldg(ed + e);
+    }
+    *reinterpret_cast<float4*>(eft + t * 4) = ef;
+  }
+  float any[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {                   // jraph.segment_softmax over the row's slots
+    float mx = sc[0][h];
+#pragma unroll
+    for (int j = 1; j < J; ++j) mx = fmaxf(mx, sc[j][h]);
+    mx = warp_max(mx);
+    float p[J], l = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) { p[j] = (sv[j] >= 0) ? expf(sc[j][h] - mx) : 0.f; l += p[j]; }
+    l = warp_sum(l);
+    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    any[h] = (l > 0.f) ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) sc[j][h] = p[j] * inv_l;
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    *reinterpret_cast<float4*>(at + (lane + 32 * j) * 4) = make_float4(sc[j][0], sc[j][1], sc[j][2], 0.f);
+  __syncwarp();
+  // weighted sender features: lane -> feature column c (INX lanes per slot group)
+  {
+    constexpr int NG = 32 / INX;                  // slot groups sharing the warp (4 for INX = 8)
+    const int c = lane % INX, tq = lane / INX;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int t = tq; t < deg; t += NG) {
+      const int s = srow[t];
+      if (s < 0) continue;
+      const float4 av = *reinterpret_cast<const float4*>(at + t * 4);
+      const float x = X[(size_t)s * XS + c];
+      a0 = fmaf(av.x, x, a0); a1 = fmaf(av.y, x, a1); a2 = fmaf(av.z, x, a2);
+    }
+#pragma unroll
+    for (int o = INX; o < 32; o <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (tq == 0 && c < IN) {
+      zc[c * RS2] = a0; zc[(INA + c) * RS2] = a1; zc[(2 * INA + c) * RS2] = a2;
+    }
+  }
+  if (lane < H * 4) {                             // weighted edge features + sum of weights
+    const int h = lane >> 2, jf = lane & 3;
+    float acc = 0.f;
+    for (int t = 0; t < deg; ++t) acc = fmaf(at[t * 4 + h], eft[t * 4 + jf], acc);
+    zc[(h * INA + IN + 1 + jf) * RS2] = acc;
+    if (jf == 0) zc[(h * INA + IN) * RS2] = (h == 0) ? any[0] : ((h == 1) ? any[1] : any[2]);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------ GNN layers
 template <int NL>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(512, 1)
 gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
   extern __shared__ __align__(16) float smem[];
+  const int nth = blockDim.x, nwarps = nth >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ws = smem;                                    // GNN weights
   float* x0 = ws + pl.w_fl;                            // [M][8]
   float* x1 = x0 + pl.x0_fl;                           // [M][36]
   float* xr = x1 + pl.x1_fl;                           // [32][RS2]
   float* q = xr + 32 * RS2;                            // [192][RS2]; z aliases it
   float* qt = q + 192 * RS2;                           // [R2][H][QTS]
-  int* sidx = reinterpret_cast<int*>(qt + R2 * H * QTS);   // [R2][deg]
-  float* sc = reinterpret_cast<float*>(sidx) + pl.sidx_fl; // [R2][H][deg]
+  int* sidx = reinterpret_cast<int*>(qt + R2 * H * QTS);   // [R2][degp]
+  float* scr = reinterpret_cast<float*>(sidx) + pl.sidx_fl;   // per-warp attention scratch
   float* z = q;
 
-  for (int i = threadIdx.x; i < pl.w_fl / 4; i += NT) cp_async16(ws + 4 * i, params + pl.w_off + 4 * i);
+  for (int i = threadIdx.x; i < pl.w_fl / 4; i += nth) cp_async16(ws + 4 * i, params + pl.w_off + 4 * i);
   cp_async_wait_all();
   __syncthreads();
   auto wptr = [&](const float* p) { return ws + ((p - params) - pl.w_off); };
 
-  const int n = g.n, N = g.N, nd = g.nd, G = g.G, deg = pl.deg;
+  const int n = g.n, N = g.N, nd = g.nd, G = g.G, deg = pl.deg, degp = pl.degp;
   const int nodes_per = N - 1, pad = N - 1;
   const int n_tiles = (g.n_graphs + G - 1) / G;
   const int nr_out = (net.kind == DGPPO_NET_VL) ? 1 : n;
+  float* my_scr = scr + (size_t)warp * degp * 8;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int tile0 = tile * G;
     const int gcount = min(G, g.n_graphs - tile0);
     const int rows = gcount * n;
-    const int M = gcount * nodes_per;
+    auto gslot_of = [&](int gl) {
+      const int gi = tile0 + gl;
+      const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+      return (size_t)env * g.pitch + slot;
+    };
     __syncthreads();
 
     // ---- stage node features (async) and the per-row sender table
-    for (int idx = threadIdx.x; idx < M * X0S; idx += NT) {
-      const int s = idx / X0S, c = idx - s * X0S;
-      if (c < nd) {
-        const int gl = s / nodes_per, node = s - gl * nodes_per;
-        const int gi = tile0 + gl;
-        const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-        cp_async4(x0 + idx, g.nodes + ((size_t)env * g.pitch + slot) * N * nd + node * nd + c);
+    for (int gl = 0; gl < gcount; ++gl) {
+      const float* src = g.nodes + gslot_of(gl) * N * nd;
+      float* dst = x0 + (size_t)gl * nodes_per * X0S;
+      if (nd == X0S) {
+        for (int j = threadIdx.x; j < nodes_per * X0S; j += nth) cp_async4(dst + j, src + j);
       } else {
-        x0[idx] = 0.f;
+        for (int j = threadIdx.x; j < nodes_per * 7; j += nth) {
+          const int node = j / 7, c = j - node * 7;
+          cp_async4(dst + node * X0S + c, src + j);
+        }
+        for (int j = threadIdx.x; j < nodes_per; j += nth) dst[j * X0S + 7] = 0.f;
       }
     }
-    for (int idx = threadIdx.x; idx < R2 * deg; idx += NT) {
-      const int r = idx / deg, t = idx - r * deg;
+    for (int idx = threadIdx.x; idx < R2 * degp; idx += nth) {
+      const int r = idx / degp, t = idx - r * degp;
       int s = -1;
-      if (r < rows) {
+      if (r < rows && t < deg) {
         const int gl = r / n, i = r - gl * n;
-        const int gi = tile0 + gl;
-        const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-        const size_t gslot = (size_t)env * g.pitch + slot;
+        const size_t gslot = gslot_of(gl);
         const int e = (t < n) ? i * n + t
                               : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
                                                   : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
@@ -168,11 +291,10 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       const LayerP& P = net.L[l];
       const int IN = P.in, D = P.d, HD = H * D, INP = round4(IN + 1), INA = IN + 5;
       const bool last = (l == NL - 1);
-      const int INX = (l == 0) ? X0S : 32;             // feature columns staged per node
       const float *wq = wptr(P.wq), *bq = wptr(P.bq), *wkt = wptr(P.wkt), *wagg = wptr(P.wagg),
                   *wu = wptr(P.wu), *bu = wptr(P.bu);
 
-      for (int idx = threadIdx.x; idx < 32 * R2; idx += NT) {       // xr[c][r] = X[node(r)][c]
+      for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // xr[c][r] = X[node(r)][c]
         const int c = idx / R2, r = idx - c * R2;
         float v = 0.f;
         if (r < rows && c < IN) { const int gl = r / n, i = r - gl * n; v = X[((size_t)gl * nodes_per + i) * XS + c]; }
@@ -180,174 +302,121 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       }
       __syncthreads();
       // q = xr Wq + bq  -> q[c][r]
-      gemm_ws<R2, RS2, 4>(xr, IN, wq, HD, 1.f, nullptr, 0, nullptr, 0, HD / 4,
-                          [&](int r0, int c0, float (&acc)[4][4]) {
+      gemm_ws<R2, RS2, 2>(xr, 0, IN, wq, HD, 1.f, nullptr, 0, nullptr, 0, HD / 4, 0, nwarps,
+                          [&](int r0, int c0, float (&acc)[2][4]) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                               const float bj = bq[c0 + j];
-                              *reinterpret_cast<float4*>(q + (c0 + j) * RS2 + r0) =
-                                  make_float4(acc[0][j] + bj, acc[1][j] + bj, acc[2][j] + bj, acc[3][j] + bj);
+                              *reinterpret_cast<float2*>(q + (c0 + j) * RS2 + r0) =
+                                  make_float2(acc[0][j] + bj, acc[1][j] + bj);
                             }
                           });
       __syncthreads();
-      // qt[r][h][:] = Wk_h^T q_h[r]  (column IN carries q_h . bk_h)
-      for (int h = 0; h < H; ++h)
-        gemm_ws<R2, RS2, 2>(q + (h * D) * RS2, D, wkt + (size_t)h * D * INP, INP, 1.f, nullptr, 0, nullptr, 0,
-                            INP / 4, [&](int r0, int c0, float (&acc)[2][4]) {
+      // qt[r][h][:] = Wk_h^T q_h[r]  (column IN carries q_h . bk_h): one (h, 2 rows, 4 cols) item per thread
+      {
+        const int ncg = INP / 4;
+        for (int item = threadIdx.x; item < H * (R2 / 2) * ncg; item += nth) {
+          const int cg = item % ncg, rg = (item / ncg) % (R2 / 2), h = item / (ncg * (R2 / 2));
+          const float* ap = q + (h * D) * RS2 + rg * 2;
+          const float* wp = wkt + (size_t)h * D * INP + cg * 4;
+          float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 8
+          for (int k = 0; k < D; ++k) {
+            const float2 a = *reinterpret_cast<const float2*>(ap + k * RS2);
+            const float4 w = *reinterpret_cast<const float4*>(wp + k * INP);
+            acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
+            acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+            acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
+          }
 #pragma unroll
-                              for (int i = 0; i < 2; ++i)
-                                *reinterpret_cast<float4*>(qt + ((r0 + i) * H + h) * QTS + c0) =
-                                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                            });
-      __syncthreads();
-      // ---- attention phase A: scores per (row, head, slot)
-      const float isd = 1.f / sqrtf((float)D);
-      for (int idx = threadIdx.x; idx < R2 * H * deg; idx += NT) {
-        const int t = idx % deg, rh = idx / deg, r = rh / H;
-        const int s = sidx[r * deg + t];
-        float v = -INFINITY;
-        if (s >= 0) {
-          const float* qp = qt + rh * QTS;
-          const float* xp = X + (size_t)s * XS;
-          float acc = qp[IN];
-          for (int c = 0; c < INX; c += 4) {
-            const float4 qv = *reinterpret_cast<const float4*>(qp + c);
-            const float4 xv = *reinterpret_cast<const float4*>(xp + c);
-            if (c < IN) acc = fmaf(qv.x, xv.x, acc);
-            if (c + 1 < IN) acc = fmaf(qv.y, xv.y, acc);
-            if (c + 2 < IN) acc = fmaf(qv.z, xv.z, acc);
-            if (c + 3 < IN) acc = fmaf(qv.w, xv.w, acc);
-          }
-          v = acc * isd;
+          for (int i = 0; i < 2; ++i)
+            *reinterpret_cast<float4*>(qt + ((rg * 2 + i) * H + h) * QTS + cg * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
-        sc[idx] = v;
       }
       __syncthreads();
-      // ---- phase B: softmax over the row's slots (jraph.segment_softmax; gnn.py:101)
-      for (int rh = threadIdx.x; rh < R2 * H; rh += NT) {
-        float* sp = sc + rh * deg;
-        float mx = -INFINITY;
-        for (int t = 0; t < deg; ++t) mx = fmaxf(mx, sp[t]);
-        float l = 0.f;
-        if (mx > -INFINITY) {
-          for (int t = 0; t < deg; ++t) { const float p = expf(sp[t] - mx); sp[t] = p; l += p; }
-          const float inv_l = 1.f / l;
-          for (int t = 0; t < deg; ++t) sp[t] *= inv_l;
-        } else {
-          for (int t = 0; t < deg; ++t) sp[t] = 0.f;
+      // ---- attention: one warp per receiver row
+      {
+        const float isd = 1.f / sqrtf((float)D);
+        for (int r = warp; r < R2; r += nwarps) {
+          const bool live = r < rows;
+          const int gl = live ? r / n : 0, ia = live ? r - gl * n : 0;
+          const float4* ed = reinterpret_cast<const float4*>(g.edges + gslot_of(gl) * g.E * 4);
+          if (l == 0) {
+            if (degp == 32) attention_row<X0S, 1>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
+                                                  X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+            else            attention_row<X0S, 2>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
+                                                  X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+          } else {
+            if (degp == 32) attention_row<32, 1>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
+                                                 X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+            else            attention_row<32, 2>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
+                                                 X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+          }
         }
-        const int r = rh / H, h = rh - r * H;
-        z[(h * INA + IN) * RS2 + r] = (l > 0.f) ? 1.f : 0.f;
       }
       __syncthreads();
-      // ---- phase C: weighted sums of sender features / edge features
-      const int ngrp = INX / 4 + 1;
-      for (int idx = threadIdx.x; idx < R2 * H * ngrp; idx += NT) {
-        const int grp = idx % ngrp, rh = idx / ngrp, r = rh / H, h = rh - r * H;
-        const float* sp = sc + rh * deg;
-        const int* si = sidx + r * deg;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (grp < ngrp - 1) {
-          for (int t = 0; t < deg; ++t) {
-            const float a = sp[t];
-            if (a == 0.f) continue;
-            const float4 xv = *reinterpret_cast<const float4*>(X + (size_t)si[t] * XS + grp * 4);
-            a0 = fmaf(a, xv.x, a0); a1 = fmaf(a, xv.y, a1); a2 = fmaf(a, xv.z, a2); a3 = fmaf(a, xv.w, a3);
-          }
-          const int c = grp * 4;
-          float* zc = z + (h * INA + c) * RS2 + r;
-          zc[0] = a0;
-          if (c + 1 < IN) zc[RS2] = a1;
-          if (c + 2 < IN) zc[2 * RS2] = a2;
-          if (c + 3 < IN) zc[3 * RS2] = a3;
-        } else {
-          if (r < rows) {
-            const int gl = r / n, i = r - gl * n;
-            const int gi = tile0 + gl;
-            const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-            const float4* ed = reinterpret_cast<const float4*>(g.edges + ((size_t)env * g.pitch + slot) * g.E * 4);
-            for (int t = 0; t < deg; ++t) {
-              const float a = sp[t];
-              if (a == 0.f) continue;
-              const int e = (t < n) ? i * n + t
-                                    : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
-                                                        : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
-              const float4 ef = __ldg(ed + e);
-              a0 = fmaf(a, ef.x, a0); a1 = fmaf(a, ef.y, a1); a2 = fmaf(a, ef.z, a2); a3 = fmaf(a, ef.w, a3);
+      // ---- x' = relu(x Wu + bu + 1/H z Wagg): split-K, the two halves of the CTA run
+      //      concurrently and leave partial sums in smem (scr / qt are dead by now):
+      //      upper warps: k in [kh, H*INA) of z Wagg; lower warps: k in [0, kh) + x Wu.
+      const int KZ = H * INA, kh = KZ / 2, hw = nwarps / 2;
+      float* part_hi = qt;                                            // [R2][64]
+      float* part_lo = scr;                                           // [R2][64]
+      auto store_part = [&](float* dstp) {
+        return [=](int r0, int c0, float (&acc)[2][4]) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            *reinterpret_cast<float4*>(dstp + (r0 + i) * 64 + c0) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        };
+      };
+      gemm_ws<R2, RS2, 2>(z, kh, KZ, wagg, D, 1.f / H, nullptr, 0, nullptr, 0, D / 4, hw, nwarps - hw,
+                          store_part(part_hi));
+      gemm_ws<R2, RS2, 2>(z, 0, kh, wagg, D, 1.f / H, xr, IN, wu, D, D / 4, 0, hw, store_part(part_lo));
+      if (!last) {                                                    // non-agent nodes (all threads)
+        for (int gl = 0; gl < gcount; ++gl) {
+          const int nn = nodes_per - n;
+          for (int idx = threadIdx.x; idx < nn * 8; idx += nth) {
+            const int s = gl * nodes_per + n + (idx >> 3), c0 = (idx & 7) * 4;
+            const float* x = X + (size_t)s * XS;
+            float a0 = bu[c0], a1 = bu[c0 + 1], a2 = bu[c0 + 2], a3 = bu[c0 + 3];
+            for (int c = 0; c < IN; ++c) {
+              const float xv = x[c];
+              const float4 w = *reinterpret_cast<const float4*>(wu + c * D + c0);
+              a0 = fmaf(xv, w.x, a0); a1 = fmaf(xv, w.y, a1); a2 = fmaf(xv, w.z, a2); a3 = fmaf(xv, w.w, a3);
             }
+            *reinterpret_cast<float4*>(x1 + (size_t)s * X1S + c0) =
+                make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
           }
-          float* zc = z + (h * INA + IN + 1) * RS2 + r;
-          zc[0] = a0; zc[RS2] = a1; zc[2 * RS2] = a2; zc[3 * RS2] = a3;
         }
       }
       __syncthreads();
-      // ---- x' = relu(x Wu + bu + 1/H z Wagg)
-      if (!last) {
-        gemm_ws<R2, RS2, 2>(z, H * INA, wagg, D, 1.f / H, xr, IN, wu, D, D / 4,
-                            [&](int r0, int c0, float (&acc)[2][4]) {
-#pragma unroll
-                              for (int i = 0; i < 2; ++i) {
-                                const int r = r0 + i;
-                                if (r < rows) {
-                                  const int gl = r / n, ia = r - gl * n;
-                                  float* dst = x1 + ((size_t)gl * nodes_per + ia) * X1S + c0;
-                                  *reinterpret_cast<float4*>(dst) =
-                                      make_float4(fmaxf(acc[i][0] + bu[c0], 0.f), fmaxf(acc[i][1] + bu[c0 + 1], 0.f),
-                                                  fmaxf(acc[i][2] + bu[c0 + 2], 0.f), fmaxf(acc[i][3] + bu[c0 + 3], 0.f));
-                                }
-                              }
-                            });
-        for (int idx = threadIdx.x; idx < M * 8; idx += NT) {           // non-agent nodes
-          const int s = idx >> 3, c0 = (idx & 7) * 4;
-          const int node = s % nodes_per;
-          if (node < n) continue;
-          const float* x = X + (size_t)s * XS;
-          float a0 = bu[c0], a1 = bu[c0 + 1], a2 = bu[c0 + 2], a3 = bu[c0 + 3];
-          for (int c = 0; c < IN; ++c) {
-            const float xv = x[c];
-            const float4 w = *reinterpret_cast<const float4*>(wu + c * D + c0);
-            a0 = fmaf(xv, w.x, a0); a1 = fmaf(xv, w.y, a1); a2 = fmaf(xv, w.z, a2); a3 = fmaf(xv, w.w, a3);
-          }
-          *reinterpret_cast<float4*>(x1 + (size_t)s * X1S + c0) =
-              make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+      float* ob = x0;                                                 // Vl only: [64][RS2] (x0 is dead by then)
+      for (int idx = threadIdx.x; idx < R2 * (D / 4); idx += nth) {   // combine + bias + relu
+        const int r = idx / (D / 4), c0 = (idx - r * (D / 4)) * 4;
+        const float4 lo = *reinterpret_cast<const float4*>(part_lo + r * 64 + c0);
+        const float4 hi = *reinterpret_cast<const float4*>(part_hi + r * 64 + c0);
+        const float4 v = make_float4(fmaxf(lo.x + hi.x + bu[c0], 0.f), fmaxf(lo.y + hi.y + bu[c0 + 1], 0.f),
+                                     fmaxf(lo.z + hi.z + bu[c0 + 2], 0.f), fmaxf(lo.w + hi.w + bu[c0 + 3], 0.f));
+        if (last && net.kind == DGPPO_NET_VL) {
+          ob[(c0 + 0) * RS2 + r] = v.x; ob[(c0 + 1) * RS2 + r] = v.y;
+          ob[(c0 + 2) * RS2 + r] = v.z; ob[(c0 + 3) * RS2 + r] = v.w;
+        } else if (r < rows) {
+          const int gl = r / n, ia = r - gl * n;
+          if (!last) *reinterpret_cast<float4*>(x1 + ((size_t)gl * nodes_per + ia) * X1S + c0) = v;
+          else       *reinterpret_cast<float4*>(g.rnn_out + (gslot_of(gl) * n + ia) * HID + c0) = v;   // scratch rows
         }
-        X = x1; XS = X1S;
-      } else if (net.kind != DGPPO_NET_VL) {
-        // final embeddings straight to the scratch rows (rnn_out layout)
-        gemm_ws<R2, RS2, 2>(z, H * INA, wagg, D, 1.f / H, xr, IN, wu, D, D / 4,
-                            [&](int r0, int c0, float (&acc)[2][4]) {
-#pragma unroll
-                              for (int i = 0; i < 2; ++i) {
-                                const int r = r0 + i;
-                                if (r < rows) {
-                                  const int gl = r / n, ia = r - gl * n;
-                                  const int gi = tile0 + gl;
-                                  const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-                                  float* dst = g.rnn_out + (((size_t)env * g.rnn_pitch + slot) * n + ia) * HID + c0;
-                                  *reinterpret_cast<float4*>(dst) =
-                                      make_float4(fmaxf(acc[i][0] + bu[c0], 0.f), fmaxf(acc[i][1] + bu[c0 + 1], 0.f),
-                                                  fmaxf(acc[i][2] + bu[c0 + 2], 0.f), fmaxf(acc[i][3] + bu[c0 + 3], 0.f));
-                                }
-                              }
-                            });
-      } else {
+      }
+      if (!last) { X = x1; XS = X1S; }
+      if (last && net.kind == DGPPO_NET_VL) {
         // centralised Vl: mean over the agents of each graph (value.py:28-31)
-        float* ob = x0;                                    // [64][RS2]; x0 is dead by now
-        gemm_ws<R2, RS2, 2>(z, H * INA, wagg, D, 1.f / H, xr, IN, wu, D, D / 4,
-                            [&](int r0, int c0, float (&acc)[2][4]) {
-#pragma unroll
-                              for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<float2*>(ob + (c0 + j) * RS2 + r0) =
-                                    make_float2(fmaxf(acc[0][j] + bu[c0 + j], 0.f), fmaxf(acc[1][j] + bu[c0 + j], 0.f));
-                            });
         __syncthreads();
-        for (int idx = threadIdx.x; idx < HID * gcount; idx += NT) {
+        for (int idx = threadIdx.x; idx < HID * gcount; idx += nth) {
           const int gl = idx / HID, c = idx - gl * HID;
           float sacc = 0.f;
           for (int i = 0; i < n; ++i) sacc += ob[c * RS2 + gl * n + i];
-          const int gi = tile0 + gl;
-          const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-          g.rnn_out[(((size_t)env * g.rnn_pitch + slot) * nr_out) * HID + c] = sacc / (float)n;
+          g.rnn_out[(gslot_of(gl) * nr_out) * HID + c] = sacc / (float)n;
         }
       }
       __syncthreads();
@@ -562,11 +631,17 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   pl.x0_fl = pl.m_cap * X0S;
   if (P.kind == DGPPO_NET_VL && pl.x0_fl < HID * RS2) pl.x0_fl = HID * RS2;
   pl.x1_fl = (P.n_layers == 2) ? pl.m_cap * X1S : 0;
-  pl.sidx_fl = round4(R2 * pl.deg);
-  pl.sc_fl = round4(R2 * H * pl.deg);
-  const size_t fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + 192 * RS2 + R2 * H * QTS +
-                    pl.sidx_fl + pl.sc_fl;
-  pl.smem_bytes = fl * sizeof(float);
+  pl.degp = ((pl.deg + 31) / 32) * 32;
+  if (pl.degp > 64) return DGPPO_V2_UNSUPPORTED;
+  pl.sidx_fl = R2 * pl.degp;
+  const size_t base_fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + 192 * RS2 + R2 * H * QTS + pl.sidx_fl;
+  pl.threads = 512;
+  pl.scr_fl = (pl.threads / 32) * pl.degp * 8;       // also hosts a [R2][64] split-K partial (2048 floats)
+  if ((base_fl + pl.scr_fl) * sizeof(float) > 227 * 1024) {
+    pl.threads = 256;
+    pl.scr_fl = (pl.threads / 32) * pl.degp * 8;
+  }
+  pl.smem_bytes = (base_fl + pl.scr_fl) * sizeof(float);
   pl.head_smem_bytes = ((size_t)pl.hw_fl + 3 * HID * RS + 4 * RS) * sizeof(float);
   if (pl.smem_bytes > 227 * 1024 || pl.head_smem_bytes > 227 * 1024) return DGPPO_V2_UNSUPPORTED;
   if ((pl.w_off & 3) || (pl.w_fl & 3) || (pl.hw_fl & 3)) return DGPPO_V2_UNSUPPORTED;
@@ -578,11 +653,11 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   if (P.n_layers == 2) {
     err = cudaFuncSetAttribute(gnn_layers_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return (int)err;
-    gnn_layers_kernel<2><<<grid1, NT, pl.smem_bytes, st>>>(P, g, pl, params);
+    gnn_layers_kernel<2><<<grid1, pl.threads, pl.smem_bytes, st>>>(P, g, pl, params);
   } else {
     err = cudaFuncSetAttribute(gnn_layers_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return (int)err;
-    gnn_layers_kernel<1><<<grid1, NT, pl.smem_bytes, st>>>(P, g, pl, params);
+    gnn_layers_kernel<1><<<grid1, pl.threads, pl.smem_bytes, st>>>(P, g, pl, params);
   }
   err = cudaGetLastError();
   if (err != cudaSuccess) return (int)err;
