@@ -214,10 +214,24 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
         float det = fsub(fmul(dx12, dy43), fmul(dy12, dx43));
         const float sg = (det > 0.f) ? 1.f : ((det < 0.f) ? -1.f : det);   // sign(0)=0, sign(NaN)=NaN
         det = fmul(sg, fminf(fmaxf(fabsf(det), 1e-7f), 1e7f));
-        const float alpha = fdiv(fsub(fmul(dy43, dx13), fmul(dx43, dy13)), det);
-        const float beta = fdiv(fadd(fmul(-dy12, dx13), fmul(dx12, dy13)), det);
-        const float vf = (alpha <= 1.f && alpha >= 0.f && beta <= 1.f && beta >= 0.f) ? 1.f : 0.f;
-        const float am = fadd(fmul(vf, alpha), fmul(fsub(1.f, vf), 1e6f));
+        const float na = fsub(fmul(dy43, dx13), fmul(dx43, dy13));
+        const float nb = fadd(fmul(-dy12, dx13), fmul(dx12, dy13));
+        // Division-free early out.  With 1e-7 <= |det| <= 1e7 the rounded quotient q = n/det is
+        // certainly > 1 when |n| > 1.0001 |det| (same sign) and certainly < 0 when the signs differ
+        // and |n| > 1e-30 (|q| >= 1e-37, it cannot round to -0): the slot is then invalid and
+        // contributes exactly 0*q + 1*1e6 = 1e6, as the literal expression would.  det == 0 or NaN
+        // (exactly parallel ray: q = +-inf / NaN) always takes the literal path below.
+        const float ad = fabsf(det);
+        const bool regular = ad >= 1e-7f;                     // false for 0 and NaN
+        const bool out_a = ((na > 0.f) == (det > 0.f)) ? (fabsf(na) > 1.0001f * ad) : (fabsf(na) > 1e-30f);
+        const bool out_b = ((nb > 0.f) == (det > 0.f)) ? (fabsf(nb) > 1.0001f * ad) : (fabsf(nb) > 1e-30f);
+        float am = 1e6f;
+        if (!(regular && (out_a || out_b))) {
+          const float alpha = fdiv(na, det);
+          const float beta = fdiv(nb, det);
+          const float vf = (alpha <= 1.f && alpha >= 0.f && beta <= 1.f && beta >= 0.f) ? 1.f : 0.f;
+          am = fadd(fmul(vf, alpha), fmul(fsub(1.f, vf), 1e6f));
+        }
         amo = nanmin(amo, am);
       }
       amin = nanmin(amin, amo);
