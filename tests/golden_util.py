@@ -1,0 +1,35 @@
+"""Loading of the reference-generated fixtures (tests/golden/ref_*.npz, made by
+tools/gen_golden_from_reference.py from the reference's own source)."""
+import os
+
+import numpy as np
+
+from oracle import env_np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GRAPH_FIELDS = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
+
+CASES = {
+    "LidarSpread_n3_obs3": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=3, n_obs=3),
+    "LidarSpread_n8_obs8": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=8, n_obs=8),
+    "LidarTarget_n5_obs2": env_np.EnvCfg(env_np.LIDAR_TARGET, n=5, n_obs=2),
+    "LidarBicycleTarget_n4_obs3": env_np.EnvCfg(env_np.LIDAR_BICYCLE_TARGET, n=4, n_obs=3),
+    "MPESpread_n8_obs3": env_np.EnvCfg(env_np.MPE_SPREAD, n=8, n_obs=3),
+    "LidarSpread_n4_obs0": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
+}
+
+
+def load(name):
+    d = np.load(os.path.join(GOLDEN_DIR, f"ref_{name}.npz"))
+    cfg = CASES[name]
+    obstacles = None
+    if "obs_center" in d.files:
+        th = d["obs_theta"].astype(np.float32)
+        obstacles = dict(center=d["obs_center"], width=d["obs_width"], height=d["obs_height"], theta=th,
+                         cos=np.cos(th).astype(np.float32), sin=np.sin(th).astype(np.float32),
+                         points=d["obs_points"])
+    return cfg, d, obstacles
+
+
+def graph_at(d, t):
+    return {k: d[k][:, t] for k in GRAPH_FIELDS}

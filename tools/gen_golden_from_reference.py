@@ -1,0 +1,101 @@
+"""Generate tests/golden/ref_*.npz by EXECUTING THE REFERENCE'S OWN SOURCE
+(/root/reference/dgppo/env/..., dgppo/algo/utils.py) under oracle/jaxshim.py
+(a NumPy stand-in for jax; jax itself is not installable in this image).
+
+    python tools/gen_golden_from_reference.py          # writes tests/golden/
+
+The fixtures hold, per env config, a few environments x a few steps of: agent /
+goal / obstacle state, the action fed to env.step, and everything env.step
+returns (all GraphsTuple arrays, reward, cost).  They travel with the repo;
+/root/reference does not exist on the GPU box.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import jaxshim  # noqa: E402
+
+jaxshim.install()
+import jax  # noqa: E402  (the shim)
+import jax.numpy as jnp  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {   # name -> (module, class, n_agents, n_obs, n_envs, n_steps)
+    "LidarSpread_n3_obs3": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 3, 3, 6, 6),
+    "LidarSpread_n8_obs8": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 8, 8, 4, 5),
+    "LidarTarget_n5_obs2": ("dgppo.env.lidar_env.lidar_target", "LidarTarget", 5, 2, 4, 5),
+    "LidarBicycleTarget_n4_obs3": ("dgppo.env.lidar_env.lidar_bicycle_target", "LidarBicycleTarget", 4, 3, 4, 5),
+    "MPESpread_n8_obs3": ("dgppo.env.mpe.mpe_spread", "MPESpread", 8, 3, 4, 5),
+    "LidarSpread_n4_obs0": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 4, 0, 3, 4),
+}
+GRAPH_FIELDS = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
+
+
+def run_case(name, mod, cls, n, n_obs, n_envs, n_steps):
+    import importlib
+    Env = getattr(importlib.import_module(mod), cls)
+    params = dict(Env.PARAMS)
+    params["n_obs"] = n_obs
+    env = Env(num_agents=n, area_size=None, max_step=128, dt=0.03, params=params)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    out = {k: [] for k in GRAPH_FIELDS}
+    out.update(action=[], reward=[], cost=[])
+    obst = {k: [] for k in ("center", "width", "height", "theta", "points")}
+    mpe_obs = []
+    for e in range(n_envs):
+        g = env.reset(jax.random.PRNGKey(100 + e))
+        es = g.env_states
+        if hasattr(es, "obstacle") and es.obstacle is not None:
+            for k in obst:
+                obst[k].append(np.asarray(getattr(es.obstacle, k)))
+        if hasattr(es, "obs") and es.obs is not None:
+            mpe_obs.append(np.asarray(es.obs))
+        per = {k: [np.asarray(getattr(g, k))] for k in GRAPH_FIELDS}
+        acts, rews, costs = [], [], []
+        for t in range(n_steps):
+            # actions beyond [-1, 1] exercise clip_action; scale grows to push agents around
+            a = rng.uniform(-1.3, 1.3, (n, 2)).astype(np.float32)
+            g, r, c, done, info = env.step(g, jnp.array(a))
+            assert not bool(done)
+            for k in GRAPH_FIELDS:
+                per[k].append(np.asarray(getattr(g, k)))
+            acts.append(a); rews.append(np.asarray(r)); costs.append(np.asarray(c))
+        for k in GRAPH_FIELDS:
+            out[k].append(np.stack(per[k]))
+        out["action"].append(np.stack(acts)); out["reward"].append(np.stack(rews)); out["cost"].append(np.stack(costs))
+    save = {k: np.stack(v) for k, v in out.items()}          # (envs, T+1 | T, ...)
+    if obst["center"]:
+        save.update({"obs_" + k: np.stack(v) for k, v in obst.items()})
+    if mpe_obs:
+        save["mpe_obs"] = np.stack(mpe_obs)
+    save["meta"] = np.array([n, n_obs, n_envs, n_steps])
+    np.savez_compressed(os.path.join(OUT, f"ref_{name}.npz"), **save)
+    print(name, {k: v.shape for k, v in save.items() if k in ("nodes", "edges", "receivers", "reward", "cost")})
+
+
+def run_gae():
+    from dgppo.algo.utils import compute_dec_ocp_gae
+    rng = np.random.default_rng(0)
+    cases = {}
+    for i, (T, a, nh) in enumerate([(16, 3, 2), (128, 8, 2), (7, 1, 1)]):
+        hs = np.clip(rng.normal(-0.7, 0.3, (T, a, nh)), -1, 1).astype(np.float32)
+        l = rng.uniform(0, 0.02, T).astype(np.float32)
+        Vh = rng.normal(0, 0.5, (T + 1, a, nh)).astype(np.float32)
+        Vl = rng.normal(0, 0.5, T + 1).astype(np.float32)
+        Qh, Ql = compute_dec_ocp_gae(jnp.array(hs), jnp.array(l), jnp.array(Vh), jnp.array(Vl), 0.99, 0.95)
+        for k, v in dict(hs=hs, l=l, Vh=Vh, Vl=Vl, Qh=np.asarray(Qh), Ql=np.asarray(Ql)).items():
+            cases[f"c{i}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "ref_gae.npz"), **cases)
+    print("gae", [k for k in cases if k.endswith("Qh")])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    for name, spec in CASES.items():
+        run_case(name, *spec)
+    run_gae()
