@@ -253,6 +253,11 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
       return (size_t)env * g.pitch + slot;
     };
+    auto rslot_of = [&](int gl) {                     // same graph in the rnn record (its own pitch)
+      const int gi = tile0 + gl;
+      const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+      return (size_t)env * g.rnn_pitch + slot;
+    };
     __syncthreads();
 
     // ---- stage node features (async) and the per-row sender table
@@ -405,7 +410,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
         } else if (r < rows) {
           const int gl = r / n, ia = r - gl * n;
           if (!last) *reinterpret_cast<float4*>(x1 + ((size_t)gl * nodes_per + ia) * X1S + c0) = v;
-          else       *reinterpret_cast<float4*>(g.rnn_out + (gslot_of(gl) * n + ia) * HID + c0) = v;   // scratch rows
+          else       *reinterpret_cast<float4*>(g.rnn_out + (rslot_of(gl) * n + ia) * HID + c0) = v;   // scratch rows
         }
       }
       if (!last) { X = x1; XS = X1S; }
@@ -416,7 +421,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
           const int gl = idx / HID, c = idx - gl * HID;
           float sacc = 0.f;
           for (int i = 0; i < n; ++i) sacc += ob[c * RS2 + gl * n + i];
-          g.rnn_out[(gslot_of(gl) * nr_out) * HID + c] = sacc / (float)n;
+          g.rnn_out[(rslot_of(gl) * nr_out) * HID + c] = sacc / (float)n;
         }
       }
       __syncthreads();
