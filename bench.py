@@ -298,9 +298,9 @@ def run_gpu(args):
                        "l2": "record written per step is %.1f GB >> 126 MB L2" % (record.nbytes() / 1e9)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": args.steps * (4 * T + 2 if lidar else 3 * T + 1),
+            "gpu_launches": args.steps * (5 * T + 2 if lidar else 4 * T + 1),   # policy = gnn_layers + head
             "clocks": clocks,
-            "roofline": {"kernel": "gnn_forward_kernel<2> (K4a policy forward)", "bound": "hbm",
+            "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel", "bound": "hbm",
                          "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                          "peak_source": which,
                          "note": "FP32-FFMA bound kernel reported against HBM as BASELINE's metric asks; "
