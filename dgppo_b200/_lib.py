@@ -34,7 +34,7 @@ class DgppoNetCfg(C.Structure):
 
 
 class DgppoNetLayout(C.Structure):
-    _fields_ = ([(k, C.c_int32 * 2) for k in ("wq", "bq", "wkt", "wagg", "wu", "bu", "in_dim", "out_dim")] +
+    _fields_ = ([(k, C.c_int32 * 2) for k in ("wqk", "wagg", "wu", "bu", "wq", "bq", "wkt", "in_dim", "out_dim")] +
                 [(k, C.c_int32) for k in ("d0w", "d0b", "ln0s", "ln0b", "d1w", "d1b", "ln1s", "ln1b",
                                           "wi", "bi", "wh", "bhn", "scale_w", "scale_b", "out_w", "out_b",
                                           "total")])

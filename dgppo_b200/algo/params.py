@@ -147,6 +147,11 @@ def pack_params(tree: Dict, cfg: _lib.DgppoNetCfg) -> np.ndarray:
         wkt[:, :, :IN] = wk.reshape(IN, Hh, D).transpose(1, 2, 0)
         wkt[:, :, IN] = _np(g["Dense_1"]["bias"]).reshape(Hh, D)
         put(L.wkt[l], wkt)
+        # merged query-key block: qt[h][c] = sum_j (x Wq_h + bq_h)[j] * wkt[h][j][c], linear in x -> one
+        # (IN+1) x (H*INP) matrix (last row = the bq part); products in double, rounded once
+        wq_aug = np.concatenate([wq, _np(g["Dense_0"]["bias"])[None]], axis=0).astype(np.float64)   # (IN+1, H*D)
+        wqk = np.einsum("chj,hjk->chk", wq_aug.reshape(IN + 1, Hh, D), wkt.astype(np.float64))      # (IN+1, H, INP)
+        put(L.wqk[l], wqk.reshape(IN + 1, Hh * INP).astype(np.float32))
         wagg = np.zeros((Hh, INA, D), np.float32)
         wagg[:, :IN, :] = wv.reshape(IN, Hh, D).transpose(1, 0, 2)
         wagg[:, IN, :] = _np(g["Dense_2"]["bias"]).reshape(Hh, D)

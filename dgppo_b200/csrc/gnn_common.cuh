@@ -13,7 +13,7 @@ constexpr int HID = 64;          // head / GRU width
 constexpr int X0S = 8;           // node-major stride of input node features
 constexpr int X1S = 36;          // node-major stride of layer-1 outputs (32 + pad)
 
-struct LayerP { const float *wq, *bq, *wkt, *wagg, *wu, *bu; int in, d; };
+struct LayerP { const float *wq, *bq, *wkt, *wagg, *wu, *bu, *wqk; int in, d; };
 
 struct NetP {
   LayerP L[2];

@@ -459,15 +459,14 @@ static int fill_layout(const DgppoNetCfg* net, DgppoNetLayout* L) {
   auto take = [&](int nfl) { int o = off; off += round4(nfl); return o; };
   for (int l = 0; l < 2; ++l) {
     if (l >= net->n_layers) {
-      L->wq[l] = L->bq[l] = L->wkt[l] = L->wagg[l] = L->wu[l] = L->bu[l] = -1;
+      L->wqk[l] = L->wagg[l] = L->wu[l] = L->bu[l] = -1;
       L->in_dim[l] = L->out_dim[l] = 0;
       continue;
     }
     const int IN = (l == 0) ? net->node_dim : 32;
     const int D = (l == net->n_layers - 1) ? 64 : 32;      // gnn.py:136
     L->in_dim[l] = IN; L->out_dim[l] = D;
-    L->wq[l] = take(IN * H * D); L->bq[l] = take(H * D);
-    L->wkt[l] = take(H * D * round4(IN + 1));
+    L->wqk[l] = take((IN + 1) * H * round4(IN + 1));
     L->wagg[l] = take(H * (IN + 5) * D);
     L->wu[l] = take(IN * D); L->bu[l] = take(D);
   }
@@ -477,6 +476,12 @@ static int fill_layout(const DgppoNetCfg* net, DgppoNetLayout* L) {
   if (net->kind == DGPPO_NET_POLICY) { L->scale_w = take(64 * 64); L->scale_b = take(64); }
   else { L->scale_w = L->scale_b = -1; }
   L->out_w = take(64 * 4); L->out_b = take(4);
+  for (int l = 0; l < 2; ++l) {                            // fallback-kernel blocks
+    if (l >= net->n_layers) { L->wq[l] = L->bq[l] = L->wkt[l] = -1; continue; }
+    const int IN = L->in_dim[l], D = L->out_dim[l];
+    L->wq[l] = take(IN * H * D); L->bq[l] = take(H * D);
+    L->wkt[l] = take(H * D * round4(IN + 1));
+  }
   L->total = off;
   return 0;
 }
@@ -498,7 +503,7 @@ static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* n
   P.n_layers = net->n_layers; P.kind = net->kind; P.n_out = net->n_out;
   for (int l = 0; l < net->n_layers; ++l) {
     P.L[l] = LayerP{params + L.wq[l], params + L.bq[l], params + L.wkt[l], params + L.wagg[l],
-                    params + L.wu[l], params + L.bu[l], L.in_dim[l], L.out_dim[l]};
+                    params + L.wu[l], params + L.bu[l], params + L.wqk[l], L.in_dim[l], L.out_dim[l]};
   }
   if (net->n_layers == 1) P.L[1] = P.L[0];
   P.d0w = params + L.d0w; P.d0b = params + L.d0b; P.ln0s = params + L.ln0s; P.ln0b = params + L.ln0b;

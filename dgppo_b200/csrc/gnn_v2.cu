@@ -115,9 +115,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Attention of ONE receiver row by ONE warp (gnn.py:100-107,114 regrouped):
-//   lane t scores slot t for the 3 heads -> warp softmax -> weights staged in the
-//   warp's scratch -> lanes turn into feature columns and accumulate the weighted
-//   sender features; 12 lanes accumulate the weighted edge features.
+//   lane t scores slot t for the 3 heads -> warp softmax -> the ACTIVE slots are
+//   compacted (ballot) into the warp's scratch as (a_0, a_1, a_2, offset of x_s)
+//   -> lanes turn into feature columns and accumulate the weighted sender features
+//   over the compacted list; 12 lanes accumulate the weighted edge features.
 // Writes column r of z[(h*INA + c)][r].
 template <int INX, int J>
 __device__ __forceinline__ void attention_row(int r, bool live, int lane, const int* srow, int deg,
@@ -130,17 +131,18 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
     for (int c = lane; c < H * INA; c += 32) zc[c * RS2] = 0.f;
     return;
   }
-  float* at = scr;                               // [degp][4]: a_h[t], h < 3
-  float* eft = scr + J * 32 * 4;                 // [degp][4]: edge features of slot t
+  float4* al = reinterpret_cast<float4*>(scr);                  // [count]: (a_0, a_1, a_2, bits(s * XS))
+  float4* eft = reinterpret_cast<float4*>(scr + J * 32 * 4);    // [count]: edge features of the slot
   int sv[J];
   float sc[J][H];
+  float4 ef[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int t = lane + 32 * j;
     sv[j] = (t < deg) ? srow[t] : -1;
 #pragma unroll
     for (int h = 0; h < H; ++h) sc[j][h] = -INFINITY;
-    float4 ef = make_float4(0.f, 0.f, 0.f, 0.f);
+    ef[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sv[j] >= 0) {
       const float* xp = X + (size_t)sv[j] * XS;
       float acc[H];
@@ -161,11 +163,9 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
       const int e = (t < n) ? i_agent * n + t
                             : ((t < n + n_ag) ? n * n + i_agent * n_ag + (t - n)
                                               : n * n + n * n_ag + i_agent * n_ao + (t - n - n_ag));
-      ef = __ldg(ed + e);
+      ef[j] = __ldg(ed + e);
     }
-    *reinterpret_cast<float4*>(eft + t * 4) = ef;
   }
-  float any[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) {                   // jraph.segment_softmax over the row's slots
     float mx = sc[0][h];
@@ -177,42 +177,49 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
     for (int j = 0; j < J; ++j) { p[j] = (sv[j] >= 0) ? expf(sc[j][h] - mx) : 0.f; l += p[j]; }
     l = warp_sum(l);
     const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-    any[h] = (l > 0.f) ? 1.f : 0.f;
 #pragma unroll
     for (int j = 0; j < J; ++j) sc[j][h] = p[j] * inv_l;
   }
+  int count = 0;
 #pragma unroll
-  for (int j = 0; j < J; ++j)
-    *reinterpret_cast<float4*>(at + (lane + 32 * j) * 4) = make_float4(sc[j][0], sc[j][1], sc[j][2], 0.f);
+  for (int j = 0; j < J; ++j) {                   // compact the active slots
+    const unsigned m = __ballot_sync(0xffffffffu, sv[j] >= 0);
+    if (sv[j] >= 0) {
+      const int pos = count + __popc(m & ((1u << lane) - 1u));
+      al[pos] = make_float4(sc[j][0], sc[j][1], sc[j][2], __int_as_float(sv[j] * XS));
+      eft[pos] = ef[j];
+    }
+    count += __popc(m);
+  }
   __syncwarp();
-  // weighted sender features: lane -> feature column c (INX lanes per slot group)
   {
     constexpr int NG = 32 / INX;                  // slot groups sharing the warp (4 for INX = 8)
     const int c = lane % INX, tq = lane / INX;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int t = tq; t < deg; t += NG) {
-      const int s = srow[t];
-      if (s < 0) continue;
-      const float4 av = *reinterpret_cast<const float4*>(at + t * 4);
-      const float x = X[(size_t)s * XS + c];
+    const int eh = (lane >> 2) % H, ej = lane & 3;    // lanes < 12: (head, edge feature)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, ae = 0.f;
+    for (int t = tq; t < count; t += NG) {
+      const float4 av = al[t];
+      const float x = X[__float_as_int(av.w) + c];
       a0 = fmaf(av.x, x, a0); a1 = fmaf(av.y, x, a1); a2 = fmaf(av.z, x, a2);
+      if (NG == 1) ae = fmaf(scr[t * 4 + eh], scr[J * 32 * 4 + t * 4 + ej], ae);
     }
+    if (NG > 1) {
 #pragma unroll
-    for (int o = INX; o < 32; o <<= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      for (int o = INX; o < 32; o <<= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (lane < H * 4)
+        for (int t = 0; t < count; ++t) ae = fmaf(scr[t * 4 + eh], scr[J * 32 * 4 + t * 4 + ej], ae);
     }
     if (tq == 0 && c < IN) {
       zc[c * RS2] = a0; zc[(INA + c) * RS2] = a1; zc[(2 * INA + c) * RS2] = a2;
     }
-  }
-  if (lane < H * 4) {                             // weighted edge features + sum of weights
-    const int h = lane >> 2, jf = lane & 3;
-    float acc = 0.f;
-    for (int t = 0; t < deg; ++t) acc = fmaf(at[t * 4 + h], eft[t * 4 + jf], acc);
-    zc[(h * INA + IN + 1 + jf) * RS2] = acc;
-    if (jf == 0) zc[(h * INA + IN) * RS2] = (h == 0) ? any[0] : ((h == 1) ? any[1] : any[2]);
+    if (lane < H * 4) {
+      zc[(eh * INA + IN + 1 + ej) * RS2] = ae;
+      if (ej == 0) zc[(eh * INA + IN) * RS2] = (count > 0) ? 1.f : 0.f;
+    }
   }
   __syncwarp();
 }
@@ -227,11 +234,12 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
   float* x0 = ws + pl.w_fl;                            // [M][8]
   float* x1 = x0 + pl.x0_fl;                           // [M][36]
   float* xr = x1 + pl.x1_fl;                           // [32][RS2]
-  float* q = xr + 32 * RS2;                            // [192][RS2]; z aliases it
-  float* qt = q + 192 * RS2;                           // [R2][H][QTS]
-  int* sidx = reinterpret_cast<int*>(qt + R2 * H * QTS);   // [R2][degp]
+  float* qt = xr + 32 * RS2;                           // [R2][H][QTS]; split-K partial after the attention
+  float* z = qt + R2 * H * QTS;                        // [112][RS2]
+  int* sidx = reinterpret_cast<int*>(z + 112 * RS2);   // [R2][degp]
   float* scr = reinterpret_cast<float*>(sidx) + pl.sidx_fl;   // per-warp attention scratch
-  float* z = q;
+  int* tab = reinterpret_cast<int*>(scr + pl.scr_fl);  // [0,32) row->graph, [32,64) row->agent, [64,96) gslot, [96,128) rslot
+  unsigned char* nflag = reinterpret_cast<unsigned char*>(tab + 128);   // [m_cap] node is an active sender
 
   for (int i = threadIdx.x; i < pl.w_fl / 4; i += nth) cp_async16(ws + 4 * i, params + pl.w_off + 4 * i);
   cp_async_wait_all();
@@ -248,21 +256,26 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
     const int tile0 = tile * G;
     const int gcount = min(G, g.n_graphs - tile0);
     const int rows = gcount * n;
-    auto gslot_of = [&](int gl) {
-      const int gi = tile0 + gl;
-      const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-      return (size_t)env * g.pitch + slot;
-    };
-    auto rslot_of = [&](int gl) {                     // same graph in the rnn record (its own pitch)
-      const int gi = tile0 + gl;
-      const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
-      return (size_t)env * g.rnn_pitch + slot;
-    };
+    const int M = gcount * nodes_per;
+    __syncthreads();
+    // ---- per-tile index tables (all later phases read these instead of dividing)
+    if (threadIdx.x < R2) {
+      const int r = threadIdx.x;
+      tab[r] = (r < rows) ? r / n : -1;
+      tab[32 + r] = (r < rows) ? r % n : 0;
+      if (r < gcount) {
+        const int gi = tile0 + r;
+        const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+        tab[64 + r] = env * g.pitch + slot;
+        tab[96 + r] = env * g.rnn_pitch + slot;
+      }
+    }
+    for (int i = threadIdx.x; i < (M + 3) / 4; i += nth) reinterpret_cast<int*>(nflag)[i] = 0;
     __syncthreads();
 
     // ---- stage node features (async) and the per-row sender table
     for (int gl = 0; gl < gcount; ++gl) {
-      const float* src = g.nodes + gslot_of(gl) * N * nd;
+      const float* src = g.nodes + (size_t)tab[64 + gl] * N * nd;
       float* dst = x0 + (size_t)gl * nodes_per * X0S;
       if (nd == X0S) {
         for (int j = threadIdx.x; j < nodes_per * X0S; j += nth) cp_async4(dst + j, src + j);
@@ -275,15 +288,19 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       }
     }
     for (int idx = threadIdx.x; idx < R2 * degp; idx += nth) {
-      const int r = idx / degp, t = idx - r * degp;
+      const int r = idx / degp, t = idx - r * degp;      // degp is 32 or 64
       int s = -1;
-      if (r < rows && t < deg) {
-        const int gl = r / n, i = r - gl * n;
-        const size_t gslot = gslot_of(gl);
+      const int gl = tab[r];
+      if (gl >= 0 && t < deg) {
+        const int i = tab[32 + r];
+        const size_t gslot = (size_t)tab[64 + gl];
         const int e = (t < n) ? i * n + t
                               : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
                                                   : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
-        if (__ldg(g.recv + gslot * g.E + e) != pad) s = gl * nodes_per + __ldg(g.send + gslot * g.E + e);
+        if (__ldg(g.recv + gslot * g.E + e) != pad) {
+          s = gl * nodes_per + __ldg(g.send + gslot * g.E + e);
+          nflag[s] = 1;
+        }
       }
       sidx[idx] = s;
     }
@@ -294,60 +311,37 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const LayerP& P = net.L[l];
-      const int IN = P.in, D = P.d, HD = H * D, INP = round4(IN + 1), INA = IN + 5;
+      const int IN = P.in, D = P.d, INP = round4(IN + 1), INA = IN + 5;
       const bool last = (l == NL - 1);
-      const float *wq = wptr(P.wq), *bq = wptr(P.bq), *wkt = wptr(P.wkt), *wagg = wptr(P.wagg),
-                  *wu = wptr(P.wu), *bu = wptr(P.bu);
+      const float *wqk = wptr(P.wqk), *wagg = wptr(P.wagg), *wu = wptr(P.wu), *bu = wptr(P.bu);
 
       for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // xr[c][r] = X[node(r)][c]
-        const int c = idx / R2, r = idx - c * R2;
+        const int c = idx >> 5, r = idx & 31;
+        const int gl = tab[r];
         float v = 0.f;
-        if (r < rows && c < IN) { const int gl = r / n, i = r - gl * n; v = X[((size_t)gl * nodes_per + i) * XS + c]; }
+        if (gl >= 0 && c < IN) v = X[((size_t)gl * nodes_per + tab[32 + r]) * XS + c];
         xr[c * RS2 + r] = v;
       }
       __syncthreads();
-      // q = xr Wq + bq  -> q[c][r]
-      gemm_ws<R2, RS2, 2>(xr, 0, IN, wq, HD, 1.f, nullptr, 0, nullptr, 0, HD / 4, 0, nwarps,
+      // qt[r][h][c] = x_r (Wq_h Wk_h^T)[:, c] + bias row  (query and key merged at pack time)
+      gemm_ws<R2, RS2, 2>(xr, 0, IN, wqk, H * INP, 1.f, nullptr, 0, nullptr, 0, H * INP / 4, 0, nwarps,
                           [&](int r0, int c0, float (&acc)[2][4]) {
+                            const int h = c0 / INP, c = c0 - h * INP;
+                            const float4 bb = *reinterpret_cast<const float4*>(wqk + IN * H * INP + c0);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                              const float bj = bq[c0 + j];
-                              *reinterpret_cast<float2*>(q + (c0 + j) * RS2 + r0) =
-                                  make_float2(acc[0][j] + bj, acc[1][j] + bj);
-                            }
+                            for (int i = 0; i < 2; ++i)
+                              *reinterpret_cast<float4*>(qt + ((r0 + i) * H + h) * QTS + c) =
+                                  make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
                           });
-      __syncthreads();
-      // qt[r][h][:] = Wk_h^T q_h[r]  (column IN carries q_h . bk_h): one (h, 2 rows, 4 cols) item per thread
-      {
-        const int ncg = INP / 4;
-        for (int item = threadIdx.x; item < H * (R2 / 2) * ncg; item += nth) {
-          const int cg = item % ncg, rg = (item / ncg) % (R2 / 2), h = item / (ncg * (R2 / 2));
-          const float* ap = q + (h * D) * RS2 + rg * 2;
-          const float* wp = wkt + (size_t)h * D * INP + cg * 4;
-          float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 8
-          for (int k = 0; k < D; ++k) {
-            const float2 a = *reinterpret_cast<const float2*>(ap + k * RS2);
-            const float4 w = *reinterpret_cast<const float4*>(wp + k * INP);
-            acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
-            acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
-            acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
-            acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
-          }
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            *reinterpret_cast<float4*>(qt + ((rg * 2 + i) * H + h) * QTS + cg * 4) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        }
-      }
       __syncthreads();
       // ---- attention: one warp per receiver row
       {
         const float isd = 1.f / sqrtf((float)D);
         for (int r = warp; r < R2; r += nwarps) {
-          const bool live = r < rows;
-          const int gl = live ? r / n : 0, ia = live ? r - gl * n : 0;
-          const float4* ed = reinterpret_cast<const float4*>(g.edges + gslot_of(gl) * g.E * 4);
+          const int gl = tab[r];
+          const bool live = gl >= 0;
+          const int ia = tab[32 + r];
+          const float4* ed = reinterpret_cast<const float4*>(g.edges + (size_t)tab[64 + (live ? gl : 0)] * g.E * 4);
           if (l == 0) {
             if (degp == 32) attention_row<X0S, 1>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
                                                   X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
@@ -379,11 +373,12 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       gemm_ws<R2, RS2, 2>(z, kh, KZ, wagg, D, 1.f / H, nullptr, 0, nullptr, 0, D / 4, hw, nwarps - hw,
                           store_part(part_hi));
       gemm_ws<R2, RS2, 2>(z, 0, kh, wagg, D, 1.f / H, xr, IN, wu, D, D / 4, 0, hw, store_part(part_lo));
-      if (!last) {                                                    // non-agent nodes (all threads)
+      if (!last) {                          // non-agent nodes that send in the next layer (all threads)
+        const int nn = nodes_per - n;
         for (int gl = 0; gl < gcount; ++gl) {
-          const int nn = nodes_per - n;
           for (int idx = threadIdx.x; idx < nn * 8; idx += nth) {
             const int s = gl * nodes_per + n + (idx >> 3), c0 = (idx & 7) * 4;
+            if (!nflag[s]) continue;
             const float* x = X + (size_t)s * XS;
             float a0 = bu[c0], a1 = bu[c0 + 1], a2 = bu[c0 + 2], a3 = bu[c0 + 3];
             for (int c = 0; c < IN; ++c) {
@@ -404,13 +399,14 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
         const float4 hi = *reinterpret_cast<const float4*>(part_hi + r * 64 + c0);
         const float4 v = make_float4(fmaxf(lo.x + hi.x + bu[c0], 0.f), fmaxf(lo.y + hi.y + bu[c0 + 1], 0.f),
                                      fmaxf(lo.z + hi.z + bu[c0 + 2], 0.f), fmaxf(lo.w + hi.w + bu[c0 + 3], 0.f));
+        const int gl = tab[r];
         if (last && net.kind == DGPPO_NET_VL) {
           ob[(c0 + 0) * RS2 + r] = v.x; ob[(c0 + 1) * RS2 + r] = v.y;
           ob[(c0 + 2) * RS2 + r] = v.z; ob[(c0 + 3) * RS2 + r] = v.w;
-        } else if (r < rows) {
-          const int gl = r / n, ia = r - gl * n;
+        } else if (gl >= 0) {
+          const int ia = tab[32 + r];
           if (!last) *reinterpret_cast<float4*>(x1 + ((size_t)gl * nodes_per + ia) * X1S + c0) = v;
-          else       *reinterpret_cast<float4*>(g.rnn_out + (rslot_of(gl) * n + ia) * HID + c0) = v;   // scratch rows
+          else       *reinterpret_cast<float4*>(g.rnn_out + ((size_t)tab[96 + gl] * n + ia) * HID + c0) = v;   // scratch rows
         }
       }
       if (!last) { X = x1; XS = X1S; }
@@ -421,7 +417,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
           const int gl = idx / HID, c = idx - gl * HID;
           float sacc = 0.f;
           for (int i = 0; i < n; ++i) sacc += ob[c * RS2 + gl * n + i];
-          g.rnn_out[(rslot_of(gl) * nr_out) * HID + c] = sacc / (float)n;
+          g.rnn_out[((size_t)tab[96 + gl] * nr_out) * HID + c] = sacc / (float)n;
         }
       }
       __syncthreads();
@@ -627,10 +623,10 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   GnnArgs g = g_in;
   g.G = R2 / g.n;
   GnnV2Plan pl;
-  pl.w_off = L.wq[0];
-  pl.w_fl = L.d0w - L.wq[0];
+  pl.w_off = L.wqk[0];
+  pl.w_fl = L.d0w - L.wqk[0];
   pl.hw_off = L.d0w;
-  pl.hw_fl = L.total - L.d0w;
+  pl.hw_fl = L.wq[0] - L.d0w;                       // up to the fallback-kernel blocks
   pl.m_cap = g.G * (g.N - 1);
   pl.deg = g.n + g.n_ag + g.n_ao;
   pl.x0_fl = pl.m_cap * X0S;
@@ -639,7 +635,8 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   pl.degp = ((pl.deg + 31) / 32) * 32;
   if (pl.degp > 64) return DGPPO_V2_UNSUPPORTED;
   pl.sidx_fl = R2 * pl.degp;
-  const size_t base_fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + 192 * RS2 + R2 * H * QTS + pl.sidx_fl;
+  const size_t base_fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + R2 * H * QTS + 112 * RS2 + pl.sidx_fl +
+                         128 /* tab */ + round4((pl.m_cap + 3) / 4) /* nflag */;
   pl.threads = 512;
   pl.scr_fl = (pl.threads / 32) * pl.degp * 8;       // also hosts a [R2][64] split-K partial (2048 floats)
   if ((base_fl + pl.scr_fl) * sizeof(float) > 227 * 1024) {

@@ -162,19 +162,23 @@ typedef struct DgppoNetCfg {
  * GraphTransformer denses named as flax auto-names them (gnn.py:86-98,110:
  * Dense_0 query on receivers, Dense_1 key on senders, Dense_2 value on
  * senders, Dense_3 edge without bias, Dense_4 update), layer l holds
- *   wq   [IN][HD]      = Dense_0.kernel             bq [HD] = Dense_0.bias
- *   wkt  [H][D][INP]   key, transposed per head with the bias folded in:
- *                        wkt[h][j][c] = Dense_1.kernel[c][h*D+j]  (c <  IN)
- *                                     = Dense_1.bias[h*D+j]       (c == IN)
- *                                     = 0                         (c >  IN)
- *                        INP = round_up(IN + 1, 4)
+ *   wqk  [IN+1][H*INP] query and key merged (both are linear in the receiver row):
+ *                        score(e) = q_h . k_h = x_r^T (Wq_h Wk_h^T) x_s + ... so with
+ *                        INP = round_up(IN + 1, 4) and column (h, c):
+ *                        wqk[c'][h*INP+c] = sum_j Dense_0.kernel[c'][h*D+j] * Dense_1.kernel[c][h*D+j]  (c < IN)
+ *                                         = sum_j Dense_0.kernel[c'][h*D+j] * Dense_1.bias[h*D+j]       (c == IN)
+ *                        row IN holds the same with Dense_0.bias in place of Dense_0.kernel[c'] (products
+ *                        formed in double at pack time); columns c > IN are 0
  *   wagg [H][INA][D]   value / edge, grouped per head, INA = IN + 1 + 4:
  *                        wagg[h][c][j] = Dense_2.kernel[c][h*D+j]      (c < IN)
  *                                      = Dense_2.bias[h*D+j]           (c == IN)
  *                                      = Dense_3.kernel[c-IN-1][h*D+j] (c > IN)
  *   wu   [IN][D]       = Dense_4.kernel             bu [D] = Dense_4.bias
+ * and, after the head/tail blocks, for the large-n fallback kernel only:
+ *   wq   [IN][HD]      = Dense_0.kernel             bq [HD] = Dense_0.bias
+ *   wkt  [H][D][INP]   wkt[h][j][c] = Dense_1.kernel[c][h*D+j] (c < IN), Dense_1.bias[h*D+j] (c == IN), 0
  * (the kernels evaluate the attention in the algebraically regrouped form
- *  score = (Wk^T q) . x_s + q . bk,  agg = sum_h Wv_h (sum_e a_e x_s) + ...,
+ *  score = x_r^T (Wq Wk^T) x_s + ...,  agg = sum_h Wv_h (sum_e a_e x_s) + ...,
  *  DESIGN.md "GNN regrouping").
  * Head (mlp.py:14-30): d0w [64][64], d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b.
  * GRU (flax GRUCell): wi = [ir|iz|in].kernel (64,192), bi = their biases
@@ -183,7 +187,8 @@ typedef struct DgppoNetCfg {
  *   [OutputDenseMean | OutputDenseStdTrans] (n_out = 2), out_b [4].
  *   value: out_w [64][4] = Dense_0.kernel zero-padded to 4 columns, out_b [4]. */
 typedef struct DgppoNetLayout {
-  int32_t wq[2], bq[2], wkt[2], wagg[2], wu[2], bu[2];
+  int32_t wqk[2], wagg[2], wu[2], bu[2];
+  int32_t wq[2], bq[2], wkt[2];                 /* fallback-kernel blocks, at the tail */
   int32_t in_dim[2], out_dim[2];
   int32_t d0w, d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b;
   int32_t wi, bi, wh, bhn;
