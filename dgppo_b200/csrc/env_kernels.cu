@@ -152,40 +152,68 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
 }
 
 // ------------------------------------------------------------------- K2
-// One warp per (environment, agent); lanes stride over rays.  Obstacle
-// records are read with warp-uniform 128-bit loads (served by L1 after the
-// first agent of the env touches them); the per-ray alpha, the stable rank
-// (counting sort over the warp's rays) and the hit points stay on chip.
+// One warp per (environment, agent).
+//   phase 1  lane = obstacle edge: the ray-independent terms of the 2x2 solve
+//            (edge vector, agent - corner, numerator of alpha) and a conservative
+//            "edge farther than the sensing range" flag go to the warp's smem;
+//   phase 2  lane = ray: loop over the edges.  A far edge can only matter when the
+//            ray is (numerically) parallel to it, so it costs one determinant;
+//            a near edge runs the literal arithmetic of obstacle.py:82-104 behind a
+//            division-free early-out;
+//   phase 3  stable top-k by counting rank over 64-bit (alpha bits, ray) keys.
+// Every value that reaches the output is produced by the same individually
+// rounded operations as the reference expression (bit-exact vs the oracle).
 constexpr int K2_WARPS = 4;
 
-__device__ __forceinline__ bool key_less(float aj, int j, float ar, int r) {
-  // stable ascending order with NaN last (jnp.argsort, env/utils.py:132)
-  const bool nj = aj != aj, nr = ar != ar;
-  if (nj || nr) return (!nj && nr) || (nj && nr && j < r);
-  return (aj < ar) || (aj == ar && j < r);
+__device__ __forceinline__ float lidar_slot_literal(float dx12, float dy12, float dx43, float dy43,
+                                                    float dx13, float dy13, float na, float det_raw) {
+  float det = det_raw;
+  const float sg = (det > 0.f) ? 1.f : ((det < 0.f) ? -1.f : det);   // sign(0)=0, sign(NaN)=NaN
+  det = fmul(sg, fminf(fmaxf(fabsf(det), 1e-7f), 1e7f));
+  const float nb = fadd(fmul(-dy12, dx13), fmul(dx12, dy13));
+  // Division-free early out.  With 1e-7 <= |det| <= 1e7 the rounded quotient q = n/det is
+  // certainly > 1 when |n| > 1.0001 |det| (same sign) and certainly < 0 when the signs differ
+  // and |n| > 1e-30 (|q| >= 1e-37, it cannot round to -0): the slot is then invalid and
+  // contributes exactly 0*q + 1*1e6 = 1e6, as the literal expression would.  det == 0 or NaN
+  // (exactly parallel ray: q = +-inf / NaN) always takes the literal path below.
+  const float ad = fabsf(det);
+  const bool regular = ad >= 1e-7f;                     // false for 0 and NaN
+  const bool out_a = ((na > 0.f) == (det > 0.f)) ? (fabsf(na) > 1.0001f * ad) : (fabsf(na) > 1e-30f);
+  const bool out_b = ((nb > 0.f) == (det > 0.f)) ? (fabsf(nb) > 1.0001f * ad) : (fabsf(nb) > 1e-30f);
+  if (regular && (out_a || out_b)) return 1e6f;
+  const float alpha = fdiv(na, det);
+  const float beta = fdiv(nb, det);
+  const float vf = (alpha <= 1.f && alpha >= 0.f && beta <= 1.f && beta >= 0.f) ? 1.f : 0.f;
+  return fadd(fmul(vf, alpha), fmul(fsub(1.f, vf), 1e6f));
 }
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ obstacles,
              const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long item = (long)blockIdx.x * K2_WARPS + warp;
-  const int n = k.n, R = k.n_rays;
+  const int n = k.n, R = k.n_rays, ne = k.n_obs * 4;
   if (item >= (long)b * n) return;
   const int env = (int)(item / n);
-  float* al = smem + warp * (3 * R);
-  float* hx = al + R;
+  const int per_warp = ne * 5 + ((ne + 3) & ~3) + 4 * R;        // floats (see the host launcher)
+  float* base = smem + (size_t)warp * per_warp;
+  float4* ed = reinterpret_cast<float4*>(base);                 // [ne] (dx43, dy43, dx13, dy13)
+  float* nav = base + 4 * ne;                                   // [ne] numerator of alpha
+  float* farf = nav + ne;                                       // [ne] 1 = edge beyond the sensing range
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(farf + ((ne + 3) & ~3));   // [R]
+  float* hx = reinterpret_cast<float*>(key + R);                // [R]
   float* hy = hx + R;
 
   const float x1 = agent[item * sd + 0], y1 = agent[item * sd + 1];
-  const float4* ob = reinterpret_cast<const float4*>(obstacles + (size_t)env * k.n_obs * DGPPO_OBS_STRIDE);
+  const float* ob = obstacles + (size_t)env * k.n_obs * DGPPO_OBS_STRIDE;
 
   // inside_obstacles(start, r=0): obstacle.py:62-72 with r = 0 reduces to
   // (rel_xx < 0 && rel_yy < 0); the corner/circle clause needs sqrt(..) < 0.
   bool in_any = false;
   for (int o = lane; o < k.n_obs; o += 32) {
-    const float4 a = ob[o * 4 + 0], c = ob[o * 4 + 1];
+    const float4 a = *reinterpret_cast<const float4*>(ob + o * DGPPO_OBS_STRIDE);
+    const float4 c = *reinterpret_cast<const float4*>(ob + o * DGPPO_OBS_STRIDE + 4);
     const float rel_x = fsub(x1, a.x), rel_y = fsub(y1, a.y);
     const float hw = fdiv(a.z, 2.f), hh = fdiv(a.w, 2.f);
     const float cs = c.y, sn = c.z;
@@ -196,57 +224,58 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   in_any = __any_sync(0xffffffffu, in_any);
   const float keep = fsub(1.f, in_any ? 1.f : 0.f);
 
+  // ---- phase 1: per-edge terms
+  const float reach = k.R * 1.002f + 1e-4f;            // a valid hit lies within comm_radius of the agent
+  for (int e = lane; e < ne; e += 32) {
+    const int o = e >> 2, q = e & 3;
+    const float* pts = ob + o * DGPPO_OBS_STRIDE + 8;
+    const float x3 = pts[2 * q], y3 = pts[2 * q + 1];
+    const float x4 = pts[2 * ((q + 3) & 3)], y4 = pts[2 * ((q + 3) & 3) + 1];
+    const float dx43 = fsub(x4, x3), dy43 = fsub(y4, y3);
+    const float dx13 = fsub(x1, x3), dy13 = fsub(y1, y3);
+    ed[e] = make_float4(dx43, dy43, dx13, dy13);
+    nav[e] = fsub(fmul(dy43, dx13), fmul(dx43, dy13));
+    // distance agent -> segment (approximate arithmetic; only used with a safety margin)
+    const float l2 = dx43 * dx43 + dy43 * dy43;
+    float t = (l2 > 0.f) ? (dx13 * dx43 + dy13 * dy43) / l2 : 0.f;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    const float cx = dx13 - t * dx43, cy = dy13 - t * dy43;
+    farf[e] = (cx * cx + cy * cy > reach * reach) ? 1.f : 0.f;
+  }
+  __syncwarp();
+
+  // ---- phase 2: per-ray minimum over the edges
   for (int r = lane; r < R; r += 32) {
     const float x2 = fadd(x1, ray_dirs[2 * r]), y2 = fadd(y1, ray_dirs[2 * r + 1]);
     const float dx12 = fsub(x1, x2), dy12 = fsub(y1, y2);
-    float amin = INFINITY;
-    for (int o = 0; o < k.n_obs; ++o) {
-      const float4 p01 = ob[o * 4 + 2], p23 = ob[o * 4 + 3];
-      const float qx[4] = {p01.x, p01.z, p23.x, p23.z};
-      const float qy[4] = {p01.y, p01.w, p23.y, p23.w};
-      float amo = INFINITY;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {                       // obstacle.py:82-104
-        const float x3 = qx[e], y3 = qy[e];
-        const float x4 = qx[(e + 3) & 3], y4 = qy[(e + 3) & 3];
-        const float dx43 = fsub(x4, x3), dy43 = fsub(y4, y3);
-        const float dx13 = fsub(x1, x3), dy13 = fsub(y1, y3);
-        float det = fsub(fmul(dx12, dy43), fmul(dy12, dx43));
-        const float sg = (det > 0.f) ? 1.f : ((det < 0.f) ? -1.f : det);   // sign(0)=0, sign(NaN)=NaN
-        det = fmul(sg, fminf(fmaxf(fabsf(det), 1e-7f), 1e7f));
-        const float na = fsub(fmul(dy43, dx13), fmul(dx43, dy13));
-        const float nb = fadd(fmul(-dy12, dx13), fmul(dx12, dy13));
-        // Division-free early out.  With 1e-7 <= |det| <= 1e7 the rounded quotient q = n/det is
-        // certainly > 1 when |n| > 1.0001 |det| (same sign) and certainly < 0 when the signs differ
-        // and |n| > 1e-30 (|q| >= 1e-37, it cannot round to -0): the slot is then invalid and
-        // contributes exactly 0*q + 1*1e6 = 1e6, as the literal expression would.  det == 0 or NaN
-        // (exactly parallel ray: q = +-inf / NaN) always takes the literal path below.
-        const float ad = fabsf(det);
-        const bool regular = ad >= 1e-7f;                     // false for 0 and NaN
-        const bool out_a = ((na > 0.f) == (det > 0.f)) ? (fabsf(na) > 1.0001f * ad) : (fabsf(na) > 1e-30f);
-        const bool out_b = ((nb > 0.f) == (det > 0.f)) ? (fabsf(nb) > 1.0001f * ad) : (fabsf(nb) > 1e-30f);
-        float am = 1e6f;
-        if (!(regular && (out_a || out_b))) {
-          const float alpha = fdiv(na, det);
-          const float beta = fdiv(nb, det);
-          const float vf = (alpha <= 1.f && alpha >= 0.f && beta <= 1.f && beta >= 0.f) ? 1.f : 0.f;
-          am = fadd(fmul(vf, alpha), fmul(fsub(1.f, vf), 1e6f));
-        }
-        amo = nanmin(amo, am);
+    float amin = 1e6f;                                  // every invalid slot contributes exactly 1e6
+    for (int e = 0; e < ne; ++e) {
+      const float4 g = ed[e];
+      const float det = fsub(fmul(dx12, g.y), fmul(dy12, g.x));
+      if (farf[e] != 0.f) {                             // warp-uniform branch
+        // beyond reach: a regular solve cannot be valid; only a (near-)parallel ray, whose
+        // determinant is clipped / zero, still has to go through the literal arithmetic
+        if (!(fabsf(det) >= 1e-7f))
+          amin = nanmin(amin, lidar_slot_literal(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det));
+      } else {
+        amin = nanmin(amin, lidar_slot_literal(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det));
       }
-      amin = nanmin(amin, amo);
     }
     const float a = fmul(amin, keep);                      // env/utils.py:129
-    al[r] = a;
+    // alpha is +0, positive or NaN: its bit pattern orders like the value; NaN sorts last;
+    // the ray index in the low bits makes the order total and stable (jnp.argsort, env/utils.py:132)
+    const unsigned bits = (a != a) ? 0xffffffffu : __float_as_uint(a);
+    key[r] = ((unsigned long long)bits << 32) | (unsigned)r;
     hx[r] = fadd(x1, fmul(fsub(x2, x1), a));               // env/utils.py:134
     hy[r] = fadd(y1, fmul(fsub(y2, y1), a));
   }
   __syncwarp();
+  // ---- phase 3: stable top-k
   float* out = hits + item * k.top_k * 2;
   for (int r = lane; r < R; r += 32) {
-    const float ar = al[r];
+    const unsigned long long kr = key[r];
     int rank = 0;
-    for (int j = 0; j < R; ++j) rank += key_less(al[j], j, ar, r) ? 1 : 0;
+    for (int j = 0; j < R; ++j) rank += (key[j] < kr) ? 1 : 0;
     if (rank < k.top_k) { out[2 * rank] = hx[r]; out[2 * rank + 1] = hy[r]; }
   }
 }
@@ -405,7 +434,9 @@ extern "C" int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg, const float* ag
   if (b == 0) return 0;
   if (b < 0 || !agent || !obstacles || !ray_dirs || !hits) return DGPPO_EINVAL;
   const EnvConsts k = make_consts(*cfg);
-  const size_t smem = (size_t)K2_WARPS * 3 * k.n_rays * sizeof(float);
+  const int ne = k.n_obs * 4;
+  const size_t smem = (size_t)K2_WARPS * (ne * 5 + ((ne + 3) & ~3) + 4 * k.n_rays) * sizeof(float);
+  if (smem > 48 * 1024) return DGPPO_ENOTSUP;
   const long items = (long)b * k.n;
   const int grid = (int)((items + K2_WARPS - 1) / K2_WARPS);
   lidar_kernel<<<grid, K2_WARPS * 32, smem, (cudaStream_t)stream>>>(
