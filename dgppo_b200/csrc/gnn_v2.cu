@@ -17,6 +17,8 @@
 //
 // Same arithmetic as v1 (GNN regrouping); attention is parallelised
 // over (row, head, edge slot) instead of (row, head).
+#include <stdlib.h>
+
 #include "gnn_common.cuh"
 
 namespace dgppo {
@@ -431,9 +433,9 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
 // warp's 8 rows of one feature) is a warp-uniform 2 x LDS.128, the weight row a
 // conflict-free LDS.32 per column: 4-6 FFMA per shared-memory wavefront, and no
 // block-wide barrier inside the tile loop (warps never exchange data).
-constexpr int WR = 8;            // rows per warp
 
 // out[c][r0..r0+7] = bias[c] + sum_k A[k][r0..r0+7] * W[k][c]   for c = lane, lane + 32
+template <int WR>
 __device__ __forceinline__ void warp_dense64(const float* A, const float* W, const float* bias,
                                              float* out, int r0, int lane) {
   float acc[WR][2];
@@ -441,10 +443,13 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
   for (int i = 0; i < WR; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
 #pragma unroll 4
   for (int k = 0; k < HID; ++k) {
-    const float4 a0 = *reinterpret_cast<const float4*>(A + k * RS + r0);
-    const float4 a1 = *reinterpret_cast<const float4*>(A + k * RS + r0 + 4);
+    float av[WR];
+#pragma unroll
+    for (int i4 = 0; i4 < WR / 4; ++i4) {
+      const float4 a = *reinterpret_cast<const float4*>(A + k * RS + r0 + 4 * i4);
+      av[4 * i4] = a.x; av[4 * i4 + 1] = a.y; av[4 * i4 + 2] = a.z; av[4 * i4 + 3] = a.w;
+    }
     const float w0 = W[k * HID + lane], w1 = W[k * HID + lane + 32];
-    const float av[WR] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
     for (int i = 0; i < WR; ++i) { acc[i][0] = fmaf(av[i], w0, acc[i][0]); acc[i][1] = fmaf(av[i], w1, acc[i][1]); }
   }
@@ -452,42 +457,46 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
   for (int j = 0; j < 2; ++j) {
     const int c = lane + 32 * j;
     const float bj = bias[c];
-    *reinterpret_cast<float4*>(out + c * RS + r0) =
-        make_float4(acc[0][j] + bj, acc[1][j] + bj, acc[2][j] + bj, acc[3][j] + bj);
-    *reinterpret_cast<float4*>(out + c * RS + r0 + 4) =
-        make_float4(acc[4][j] + bj, acc[5][j] + bj, acc[6][j] + bj, acc[7][j] + bj);
+#pragma unroll
+    for (int i4 = 0; i4 < WR / 4; ++i4)
+      *reinterpret_cast<float4*>(out + c * RS + r0 + 4 * i4) =
+          make_float4(acc[4 * i4][j] + bj, acc[4 * i4 + 1][j] + bj, acc[4 * i4 + 2][j] + bj, acc[4 * i4 + 3][j] + bj);
   }
 }
 
 // LayerNorm (flax: eps 1e-6, fast variance) + ReLU over the 64 features of the
 // warp's 8 rows; 4 lanes per row, features interleaved.
+template <int WR>
 __device__ __forceinline__ void warp_layernorm_relu(float* y, const float* scale, const float* bias,
                                                     int r0, int lane) {
-  const int r = r0 + (lane >> 2), part = lane & 3;
+  constexpr int LPR = 32 / WR;                       // lanes per row (4 or 8)
+  const int r = r0 + lane / LPR, part = lane % LPR;
   float s = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HID / 4; ++i) { const float v = y[(i * 4 + part) * RS + r]; s += v; s2 = fmaf(v, v, s2); }
-  s += __shfl_xor_sync(0xffffffffu, s, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  for (int i = 0; i < HID / LPR; ++i) { const float v = y[(i * LPR + part) * RS + r]; s += v; s2 = fmaf(v, v, s2); }
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   const float mean = s * (1.f / HID), mean2 = s2 * (1.f / HID);
   const float var = fmaxf(0.f, mean2 - mean * mean);
   const float rstd = 1.f / sqrtf(var + 1e-6f);
 #pragma unroll
-  for (int i = 0; i < HID / 4; ++i) {
-    const int c = i * 4 + part;
+  for (int i = 0; i < HID / LPR; ++i) {
+    const int c = i * LPR + part;
     y[c * RS + r] = fmaxf((y[c * RS + r] - mean) * (rstd * scale[c]) + bias[c], 0.f);
   }
 }
 
-__global__ void __launch_bounds__(NT, 1)
+template <int WR>
+__global__ void __launch_bounds__(64 / WR * 32, 1)
 head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
+  constexpr int NTH = 64 / WR * 32;                   // 64 rows per CTA: 8 warps x 8 rows or 16 warps x 4 rows
   extern __shared__ __align__(16) float smem[];
   float* ws = smem;                                   // head / GRU / tail weights
   float* y0 = ws + pl.hw_fl;                          // [64][RS]
   float* y1 = y0 + HID * RS;
   float* hbuf = y1 + HID * RS;
   float* o4 = hbuf + HID * RS;                        // [4][RS]
-  for (int i = threadIdx.x; i < pl.hw_fl / 4; i += NT) cp_async16(ws + 4 * i, params + pl.hw_off + 4 * i);
+  for (int i = threadIdx.x; i < pl.hw_fl / 4; i += NTH) cp_async16(ws + 4 * i, params + pl.hw_off + 4 * i);
   cp_async_wait_all();
   __syncthreads();
   auto wptr = [&](const float* p) { return ws + ((p - params) - pl.hw_off); };
@@ -511,7 +520,7 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
     return (((size_t)env * g.rnn_pitch + slot) * nr + i) * HID;
   };
 
-  for (long wt = (long)blockIdx.x * (NT / 32) + warp; wt < n_wtiles; wt += (long)gridDim.x * (NT / 32)) {
+  for (long wt = (long)blockIdx.x * (NTH / 32) + warp; wt < n_wtiles; wt += (long)gridDim.x * (NTH / 32)) {
     const long row0 = wt * WR;
     const int rows = (int)min((long)WR, total_rows - row0);
     __syncwarp();
@@ -531,13 +540,13 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
     cp_async_wait_all();
     __syncwarp();
     // head MLP: 2 x [Dense64 -> LayerNorm -> ReLU]   (mlp.py:14-30)
-    warp_dense64(y0, d0w, d0b, y1, r0, lane);
+    warp_dense64<WR>(y0, d0w, d0b, y1, r0, lane);
     __syncwarp();
-    warp_layernorm_relu(y1, ln0s, ln0b, r0, lane);
+    warp_layernorm_relu<WR>(y1, ln0s, ln0b, r0, lane);
     __syncwarp();
-    warp_dense64(y1, d1w, d1b, y0, r0, lane);
+    warp_dense64<WR>(y1, d1w, d1b, y0, r0, lane);
     __syncwarp();
-    warp_layernorm_relu(y0, ln1s, ln1b, r0, lane);
+    warp_layernorm_relu<WR>(y0, ln1s, ln1b, r0, lane);
     __syncwarp();
     // GRU cell (flax GRUCell; rnn.py:19-21): 8 rows x units {lane, lane+32} x 3 gates
     {
@@ -548,12 +557,14 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
         for (int i = 0; i < WR; ++i) { ai[t][i][0] = ai[t][i][1] = 0.f; ah[t][i][0] = ah[t][i][1] = 0.f; }
 #pragma unroll 2
       for (int k = 0; k < HID; ++k) {
-        const float4 x0v = *reinterpret_cast<const float4*>(y0 + k * RS + r0);
-        const float4 x1v = *reinterpret_cast<const float4*>(y0 + k * RS + r0 + 4);
-        const float4 h0v = *reinterpret_cast<const float4*>(hbuf + k * RS + r0);
-        const float4 h1v = *reinterpret_cast<const float4*>(hbuf + k * RS + r0 + 4);
-        const float xv[WR] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
-        const float hv[WR] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+        float xv[WR], hv[WR];
+#pragma unroll
+        for (int i4 = 0; i4 < WR / 4; ++i4) {
+          const float4 xa = *reinterpret_cast<const float4*>(y0 + k * RS + r0 + 4 * i4);
+          const float4 ha = *reinterpret_cast<const float4*>(hbuf + k * RS + r0 + 4 * i4);
+          xv[4 * i4] = xa.x; xv[4 * i4 + 1] = xa.y; xv[4 * i4 + 2] = xa.z; xv[4 * i4 + 3] = xa.w;
+          hv[4 * i4] = ha.x; hv[4 * i4 + 1] = ha.y; hv[4 * i4 + 2] = ha.z; hv[4 * i4 + 3] = ha.w;
+        }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
           const float wi0 = wi[k * 192 + t * 64 + lane], wi1 = wi[k * 192 + t * 64 + lane + 32];
@@ -578,8 +589,10 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
           const float cand = tanhf(ai[2][i][j] + bin + rgate * (ah[2][i][j] + bh));
           hn[i] = (1.f - zgate) * cand + zgate * hprev;
         }
-        *reinterpret_cast<float4*>(y1 + c * RS + r0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        *reinterpret_cast<float4*>(y1 + c * RS + r0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+#pragma unroll
+        for (int i4 = 0; i4 < WR / 4; ++i4)
+          *reinterpret_cast<float4*>(y1 + c * RS + r0 + 4 * i4) =
+              make_float4(hn[4 * i4], hn[4 * i4 + 1], hn[4 * i4 + 2], hn[4 * i4 + 3]);
         // new carry -> rnn_out (overwrites the scratch embeddings); coalesced across lanes
 #pragma unroll
         for (int i = 0; i < WR; ++i)
@@ -589,16 +602,18 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
     __syncwarp();
     const float* feat = y1;
     if (policy) {
-      warp_dense64(y1, scale_w, scale_b, y0, r0, lane);       // ScaleHid (policy.py:67)
+      warp_dense64<WR>(y1, scale_w, scale_b, y0, r0, lane);       // ScaleHid (policy.py:67)
       __syncwarp();
       feat = y0;
     }
     {   // out: [64] -> 4 columns; lane = (row, column)
       const int rr = lane >> 2, col = lane & 3;
-      float acc = out_b[col];
+      if (rr < WR) {
+        float acc = out_b[col];
 #pragma unroll 8
-      for (int k = 0; k < HID; ++k) acc = fmaf(feat[k * RS + r0 + rr], out_w[k * 4 + col], acc);
-      o4[col * RS + r0 + rr] = acc;
+        for (int k = 0; k < HID; ++k) acc = fmaf(feat[k * RS + r0 + rr], out_w[k * 4 + col], acc);
+        o4[col * RS + r0 + rr] = acc;
+      }
     }
     __syncwarp();
     if (lane < rows) {
@@ -667,9 +682,16 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   const long total_rows = (long)g.n_graphs * nr;
   const long h_tiles = (total_rows + R - 1) / R;             // CTAs worth of 8-row warp tiles
   const int grid2 = h_tiles < sms ? (int)h_tiles : sms;
-  err = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.head_smem_bytes);
-  if (err != cudaSuccess) return (int)err;
-  head_kernel<<<grid2, NT, pl.head_smem_bytes, st>>>(P, g, pl, params);
+  const char* wr8 = getenv("DGPPO_HEAD_WR8");
+  if (wr8 && wr8[0] == '1') {
+    err = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.head_smem_bytes);
+    if (err != cudaSuccess) return (int)err;
+    head_kernel<8><<<grid2, 256, pl.head_smem_bytes, st>>>(P, g, pl, params);
+  } else {
+    err = cudaFuncSetAttribute(head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.head_smem_bytes);
+    if (err != cudaSuccess) return (int)err;
+    head_kernel<4><<<grid2, 512, pl.head_smem_bytes, st>>>(P, g, pl, params);
+  }
   return (int)cudaGetLastError();
 }
 
