@@ -26,7 +26,7 @@ import torch
 from .. import _lib
 from ..env.base import MultiAgentEnv, ptr, require_cuda, stream_ptr
 from ..trainer.data import Rollout
-from ..trainer.rollout import RNN_DIM, run_rollout
+from ..trainer.rollout import RNN_DIM, run_rollout, run_rollout_chunked
 from ..utils.graph import GraphsTuple
 from . import params as P
 from .base import Algorithm
@@ -91,6 +91,8 @@ class DGPPO(Algorithm):
         self._gen.manual_seed(seed)
         self._np_rng = np.random.default_rng(seed)
         self.last_prepass: Optional[dict] = None
+        # independent env groups run on separate streams so env kernels overlap policy kernels
+        self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "2"))
 
     # ------------------------------------------------------------ config / params
     @property
@@ -182,15 +184,16 @@ class DGPPO(Algorithm):
         b, T = graph0.nodes.shape[0], self._env.max_episode_steps
         if eps is None:
             eps = self._eps_from_key(b_key, (b, T, self.n_agents, self.action_dim))
-        return run_rollout(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
-                           self.init_rnn_state, record=record, prof=prof)
+        return run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
+                                   self.init_rnn_state, record=record, n_chunks=self.rollout_chunks, prof=prof)
 
     def det_rollout_fn(self, params: dict, b_key, graph0: Optional[GraphsTuple] = None, record=None) -> Rollout:
         """DGPPO.det_rollout_fn (dgppo.py:108-117): test_rollout with algo.act."""
         if graph0 is None:
             graph0 = self._env.reset(b_key)
-        return run_rollout(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
-                           self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True)
+        return run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
+                                   self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True,
+                                   n_chunks=self.rollout_chunks)
 
     @staticmethod
     def _record_arrays(rollout: Rollout):

@@ -23,8 +23,8 @@
 
 namespace dgppo {
 
-constexpr int R2 = 32;           // agent rows per GNN tile
-constexpr int RS2 = 36;          // row stride of the GNN tile's transposed buffers
+constexpr int R2 = 16;           // agent rows per GNN tile (two CTAs per SM)
+constexpr int RS2 = 16;          // row stride of the GNN tile's transposed buffers
 constexpr int QTS = 36;          // per-(row, head) stride of the regrouped keys
 
 __device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
@@ -228,7 +228,7 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
 
 // ------------------------------------------------------------ GNN layers
 template <int NL>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256, 2)
 gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
   extern __shared__ __align__(16) float smem[];
   const int nth = blockDim.x, nwarps = nth >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -318,7 +318,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       const float *wqk = wptr(P.wqk), *wagg = wptr(P.wagg), *wu = wptr(P.wu), *bu = wptr(P.bu);
 
       for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // xr[c][r] = X[node(r)][c]
-        const int c = idx >> 5, r = idx & 31;
+        const int c = idx / R2, r = idx % R2;
         const int gl = tab[r];
         float v = 0.f;
         if (gl >= 0 && c < IN) v = X[((size_t)gl * nodes_per + tab[32 + r]) * XS + c];
@@ -652,12 +652,9 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   pl.sidx_fl = R2 * pl.degp;
   const size_t base_fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + R2 * H * QTS + 112 * RS2 + pl.sidx_fl +
                          128 /* tab */ + round4((pl.m_cap + 3) / 4) /* nflag */;
-  pl.threads = 512;
+  pl.threads = 256;
   pl.scr_fl = (pl.threads / 32) * pl.degp * 8;       // also hosts a [R2][64] split-K partial (2048 floats)
-  if ((base_fl + pl.scr_fl) * sizeof(float) > 227 * 1024) {
-    pl.threads = 256;
-    pl.scr_fl = (pl.threads / 32) * pl.degp * 8;
-  }
+  if (pl.scr_fl < R2 * 64) pl.scr_fl = R2 * 64;      // split-K partial [R2][64]
   pl.smem_bytes = (base_fl + pl.scr_fl) * sizeof(float);
   pl.head_smem_bytes = ((size_t)pl.hw_fl + 3 * HID * RS + 4 * RS) * sizeof(float);
   if (pl.smem_bytes > 227 * 1024 || pl.head_smem_bytes > 227 * 1024) return DGPPO_V2_UNSUPPORTED;
@@ -665,7 +662,7 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
 
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
-  const int grid1 = n_tiles < sms ? n_tiles : sms;
+  const int grid1 = n_tiles < 2 * sms ? n_tiles : 2 * sms;
   cudaError_t err;
   if (P.n_layers == 2) {
     err = cudaFuncSetAttribute(gnn_layers_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);

@@ -60,6 +60,21 @@ class RolloutRecord:
             ts.append(self.log_pis)
         return sum(t.numel() * t.element_size() for t in ts)
 
+    _TENSORS = ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge", "rnn",
+                "actions", "log_pis", "rewards", "costs", "dones", "hits_ws")
+
+    def env_slice(self, lo: int, hi: int) -> "RolloutRecord":
+        """A view of environments [lo, hi) of this record (shares memory)."""
+        v = object.__new__(RolloutRecord)
+        v.env, v.T, v.d, v.n, v.b = self.env, self.T, self.d, self.n, hi - lo
+        for k in self._TENSORS:
+            t = getattr(self, k)
+            setattr(v, k, None if t is None else t[lo:hi])
+        # the ping-pong state workspace must be contiguous per chunk: give the view its own
+        v.agent_ws = torch.empty((2, hi - lo) + tuple(self.agent_ws.shape[2:]), dtype=torch.float32,
+                                 device=self.agent_ws.device)
+        return v
+
     def graph_view(self, lo: int, hi: int, env_states) -> GraphsTuple:
         s = slice(lo, hi)
         return GraphsTuple(self.n_node[:, s], self.n_edge[:, s], self.nodes[:, s], self.edges[:, s],
@@ -133,3 +148,54 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
         rewards=rec.rewards, costs=rec.costs, dones=rec.dones,
         log_pis=rec.log_pis if eps is not None else None,
         next_graph=rec.graph_view(1, T + 1, env_view(1, T + 1)))
+
+
+def _slice_env_states(es, lo, hi):
+    if isinstance(es, LidarEnvState):
+        ob = es.obstacle
+        if ob is not None:
+            ob = type(ob)(*[t[lo:hi] for t in ob])
+        return LidarEnvState(es.agent[lo:hi], es.goal[lo:hi], ob)
+    return MPEEnvState(es.agent[lo:hi], es.goal[lo:hi], None if es.obs is None else es.obs[lo:hi])
+
+
+def run_rollout_chunked(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state=None, record=None,
+                        test_mode=False, n_chunks: int = 2, prof=None) -> Rollout:
+    """Same as run_rollout, with the environments split into `n_chunks` contiguous
+    groups that run on separate CUDA streams: the groups are independent
+    (informarl.py:183-184), so one group's env kernels (K1-K3, small, issue-bound)
+    overlap the other group's policy kernels (latency-bound, one CTA per SM)."""
+    b = graph0.nodes.shape[0]
+    dev = graph0.nodes.device
+    if n_chunks <= 1 or b < 2 * n_chunks:
+        return run_rollout(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state, record, test_mode, prof)
+    if record is None:
+        record = RolloutRecord(env, b, T, dev, stochastic=eps is not None)
+    if not hasattr(record, "_chunks") or len(record._chunks) != n_chunks:
+        bounds = [(i * b) // n_chunks for i in range(n_chunks + 1)]
+        record._chunks = [(lo, hi, record.env_slice(lo, hi), torch.cuda.Stream(device=dev))
+                          for lo, hi in zip(bounds[:-1], bounds[1:])]
+    cur = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(cur)
+    for i, (lo, hi, sub, st) in enumerate(record._chunks):
+        st.wait_event(start)
+        with torch.cuda.stream(st):
+            g0 = graph0.map_arrays(lambda t: t[lo:hi])._replace(env_states=_slice_env_states(graph0.env_states, lo, hi))
+            run_rollout(env, net_cfg, params_dev, g0, None if eps is None else eps[lo:hi], T, init_rnn_state,
+                        sub, test_mode, prof if i == 0 else None)
+        done = torch.cuda.Event()
+        done.record(st)
+        cur.wait_event(done)
+    rec, n, es = record, env.num_agents, graph0.env_states
+
+    def env_view(lo, hi):
+        stt = rec.states[:, lo:hi]
+        if isinstance(es, LidarEnvState):
+            return LidarEnvState(stt[:, :, :n], stt[:, :, n:2 * n], es.obstacle)
+        return MPEEnvState(stt[:, :, :n], stt[:, :, n:2 * n], es.obs)
+    rnn = rec.rnn[:, 1:] if test_mode else rec.rnn[:, :T]
+    return Rollout(graph=rec.graph_view(0, T, env_view(0, T)), actions=rec.actions,
+                   rnn_states=rnn.unsqueeze(2).unsqueeze(4), rewards=rec.rewards, costs=rec.costs, dones=rec.dones,
+                   log_pis=rec.log_pis if eps is not None else None,
+                   next_graph=rec.graph_view(1, T + 1, env_view(1, T + 1)))
