@@ -33,3 +33,24 @@ def load(name):
 
 def graph_at(d, t):
     return {k: d[k][:, t] for k in GRAPH_FIELDS}
+
+
+NN_CASES = {"LidarSpread_n3_obs3": 7, "LidarBicycleTarget_n4_obs3": 8, "MPESpread_n8_obs3": 7}
+
+
+def load_nn(name):
+    """Reference network fixture: graphs, carries, draws, outputs and the three flax-shaped
+    parameter pytrees (rebuilt from the flattened 'param:<net>:<path>' entries)."""
+    d = np.load(os.path.join(GOLDEN_DIR, f"ref_nn_{name}.npz"))
+    trees = {"policy": {}, "vh": {}, "vl": {}}
+    for key in d.files:
+        if not key.startswith("param:"):
+            continue
+        _, tag, path = key.split(":", 2)
+        node = trees[tag]
+        parts = path.split("/")
+        for p_ in parts[:-1]:
+            node = node.setdefault(p_, {})
+        node[parts[-1]] = d[key]
+    graph = {k: d[k] for k in ("nodes", "edges", "receivers", "senders")}
+    return CASES[name], d, graph, trees

@@ -188,3 +188,28 @@ def test_algo_api_act_step_collect_update():
 def GraphsTupleAt(g, t):
     from dgppo_b200.utils.graph import GraphsTuple
     return GraphsTuple(*[x[:, t].contiguous() if isinstance(x, torch.Tensor) else None for x in g])
+
+
+@pytest.mark.parametrize("name", list(G.NN_CASES))
+@pytest.mark.parametrize("gen", ["v2", "v1"])
+def test_network_kernels_match_reference_fixtures(name, gen, monkeypatch):
+    """CUDA policy / Vh / Vl forward vs outputs of the reference's own module code."""
+    from dgppo_b200 import _lib
+    from dgppo_b200.algo import params as P
+    monkeypatch.setenv("DGPPO_FORCE_V1", "1" if gen == "v1" else "0")
+    cfg, d, graph, trees = G.load_nn(name)
+    nd = G.NN_CASES[name]
+    pc = P.net_cfg(_lib.NET_POLICY, nd, 4, 2, 2)
+    a, _, h = util.k_policy(cfg, pc, P.pack_params(trees["policy"], pc), graph, d["rnn"], None)
+    np.testing.assert_allclose(a, d["act_mode"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(h, d["rnn_out"], rtol=1e-5, atol=1e-5)
+    a, lp, _ = util.k_policy(cfg, pc, P.pack_params(trees["policy"], pc), graph, d["rnn"], d["eps"])
+    np.testing.assert_allclose(a, d["act_sample"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(lp, d["log_pi"], rtol=1e-5, atol=2e-5)
+    vc = P.net_cfg(_lib.NET_VH, nd, 4, 1, 2)
+    vh, _ = util.k_value(cfg, vc, P.pack_params(trees["vh"], vc), graph, d["rnn"])
+    np.testing.assert_allclose(vh, d["vh"], rtol=1e-5, atol=1e-5)
+    lc = P.net_cfg(_lib.NET_VL, nd, 4, 2, 1)
+    vl, vlh = util.k_value(cfg, lc, P.pack_params(trees["vl"], lc), graph, d["vl_rnn"])
+    np.testing.assert_allclose(vl, d["vl"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(vlh, d["vl_rnn_out"], rtol=1e-5, atol=1e-5)

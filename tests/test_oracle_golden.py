@@ -53,3 +53,28 @@ def test_gae_matches_reference():
         Qh, Ql = algo_np.compute_dec_ocp_gae(d[f"c{i}_hs"], d[f"c{i}_l"], d[f"c{i}_Vh"], d[f"c{i}_Vl"], 0.99, 0.95)
         np.testing.assert_allclose(Qh, d[f"c{i}_Qh"], rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(Ql, d[f"c{i}_Ql"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", list(G.NN_CASES))
+def test_networks_match_reference_modules(name):
+    """Oracle vs the reference's own nn/gnn.py, nn/mlp.py, nn/rnn.py, policy.py, value.py and
+    distribution.py executed under oracle/flaxshim.py: pins the COMPOSITION (which node feeds
+    q/k/v, head order, module naming, carry wiring, thresholded log-prob)."""
+    from oracle import nn_np
+    cfg, d, graph, trees = G.load_nn(name)
+    n = cfg.n
+    # flax auto-naming as the reference builds it (SURVEY.md A.4): the GRU sits under GRUCell_1
+    assert list(trees["policy"]["params"]["PolicyNet_0"]["RNN_0"]) == ["GRUCell_1"]
+    assert set(trees["policy"]["params"]) == {"PolicyNet_0", "ScaleHid", "OutputDenseMean", "OutputDenseStdTrans"}
+    assert set(trees["vh"]["params"]) == {"GraphTransformerGNN_0", "ValueGNNHead", "RNN_0", "Dense_0"}
+    a, _, h, _ = nn_np.policy_forward(trees["policy"], graph, d["rnn"], n, None, 2)
+    np.testing.assert_allclose(a, d["act_mode"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(h, d["rnn_out"], rtol=1e-5, atol=2e-6)
+    a, lp, _, _ = nn_np.policy_forward(trees["policy"], graph, d["rnn"], n, d["eps"], 2)
+    np.testing.assert_allclose(a, d["act_sample"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(lp, d["log_pi"], rtol=1e-5, atol=5e-6)
+    vh = nn_np.vh_forward(trees["vh"], graph, d["rnn"], n, 1)
+    np.testing.assert_allclose(vh, d["vh"], rtol=1e-5, atol=2e-6)
+    vl, vlh = nn_np.vl_forward(trees["vl"], graph, d["vl_rnn"], n, 2)
+    np.testing.assert_allclose(vl, d["vl"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(vlh, d["vl_rnn_out"], rtol=1e-5, atol=2e-6)

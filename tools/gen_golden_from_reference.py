@@ -16,9 +16,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import jaxshim  # noqa: E402
+from oracle import flaxshim, jaxshim  # noqa: E402
 
-jaxshim.install()
+flaxshim.install()      # jaxshim + flax.linen / jraph / tfp stand-ins
 import jax  # noqa: E402  (the shim)
 import jax.numpy as jnp  # noqa: E402
 
@@ -94,8 +94,76 @@ def run_gae():
     print("gae", [k for k in cases if k.endswith("Qh")])
 
 
+def _flatten(tree, pre=""):
+    out = {}
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            out.update(_flatten(v, pre + k + "/"))
+        else:
+            out[pre + k] = np.asarray(v, np.float32)
+    return out
+
+
+def run_nn():
+    """Policy (mode + sample + log_pi), Vh and Vl forward of the reference's own module code
+    (nn/gnn.py, nn/mlp.py, nn/rnn.py, algo/module/{policy,value,distribution}.py) under the
+    flax / jraph / tfp stand-ins, on graphs taken from the env fixtures."""
+    from dgppo.algo.module.policy import PPOPolicy
+    from dgppo.algo.module.value import ValueNet
+    from dgppo.utils.graph import GraphsTuple
+    for name, n, node_dim in (("LidarSpread_n3_obs3", 3, 7), ("LidarBicycleTarget_n4_obs3", 4, 8),
+                              ("MPESpread_n8_obs3", 8, 7)):
+        d = np.load(os.path.join(OUT, f"ref_{name}.npz"))
+        nominal = GraphsTuple(nodes=jnp.zeros((n, node_dim)), edges=jnp.zeros((n, 4)), states=jnp.zeros((n, 4)),
+                              n_node=jnp.array(n), n_edge=jnp.array(n), senders=jnp.arange(n),
+                              receivers=jnp.arange(n), node_type=jnp.zeros((n,)), env_states=jnp.zeros((n,)))
+        rnn0 = jnp.zeros((1, n, 1, 64))
+        pol = PPOPolicy(node_dim=node_dim, edge_dim=4, n_agents=n, action_dim=2, use_rnn=True, rnn_layers=1,
+                        gnn_layers=2, gnn_out_dim=64)
+        p_pol = pol.dist.init(jax.random.PRNGKey(1), nominal, rnn0, n)
+        Vh = ValueNet(node_dim=node_dim, edge_dim=4, n_agents=n, n_out=2, use_rnn=True, gnn_layers=1,
+                      gnn_out_dim=64, use_lstm=False, decompose=True, use_global_info=False, n_heads=3)
+        p_vh = Vh.net.init(jax.random.PRNGKey(2), nominal, rnn0, n)
+        Vl = ValueNet(node_dim=node_dim, edge_dim=4, n_agents=n, use_rnn=True, rnn_layers=1, gnn_layers=2,
+                      gnn_out_dim=64, use_lstm=False, decompose=False)
+        p_vl = Vl.net.init(jax.random.PRNGKey(3), nominal, jnp.zeros((1, 1, 1, 64)), n)
+        rng = np.random.default_rng(7)
+        E, T1 = d["nodes"].shape[0], d["nodes"].shape[1]
+        sel = [(e, t) for e in range(E) for t in (0, T1 - 1)]
+        out = {k: [] for k in ("nodes", "edges", "receivers", "senders", "rnn", "eps", "act_mode", "rnn_out",
+                               "act_sample", "log_pi", "vh", "vl_rnn", "vl", "vl_rnn_out")}
+        for e, t in sel:
+            G = GraphsTuple(nodes=jnp.array(d["nodes"][e, t]), edges=jnp.array(d["edges"][e, t]),
+                            states=jnp.array(d["states"][e, t]), n_node=jnp.array(d["n_node"][e, t]),
+                            n_edge=jnp.array(d["n_edge"][e, t]), senders=jnp.array(d["senders"][e, t]),
+                            receivers=jnp.array(d["receivers"][e, t]), node_type=jnp.array(d["node_type"][e, t]),
+                            env_states=None)
+            rnn = (rng.standard_normal((1, n, 1, 64)) * 0.5).astype(np.float32)
+            a_mode, rnn_out = pol.get_action(p_pol, G, jnp.array(rnn))
+            key = jax.random.PRNGKey(1000 + 17 * e + t)
+            a_s, lp, rnn_out2 = pol.sample_action(p_pol, G, jnp.array(rnn), key)
+            assert np.array_equal(np.asarray(rnn_out), np.asarray(rnn_out2))
+            eps = jaxshim._gen(key).standard_normal((n, 2)).astype(np.float32)     # the draw Normal.sample made
+            vh, _ = Vh.get_value(p_vh, G, jnp.array(rnn))
+            vl_rnn = (rng.standard_normal((1, 1, 1, 64)) * 0.5).astype(np.float32)
+            vl, vl_rnn_out = Vl.get_value(p_vl, G, jnp.array(vl_rnn))
+            for k, v in dict(nodes=d["nodes"][e, t], edges=d["edges"][e, t], receivers=d["receivers"][e, t],
+                             senders=d["senders"][e, t], rnn=rnn.reshape(n, 64), eps=eps, act_mode=a_mode,
+                             rnn_out=np.asarray(rnn_out).reshape(n, 64), act_sample=a_s, log_pi=lp, vh=vh,
+                             vl_rnn=vl_rnn.reshape(64), vl=np.asarray(vl).reshape(()),
+                             vl_rnn_out=np.asarray(vl_rnn_out).reshape(64)).items():
+                out[k].append(np.asarray(v))
+        save = {k: np.stack(v) for k, v in out.items()}
+        for tag, tree in (("policy", p_pol), ("vh", p_vh), ("vl", p_vl)):
+            for k, v in _flatten(tree).items():
+                save[f"param:{tag}:{k}"] = v
+        np.savez_compressed(os.path.join(OUT, f"ref_nn_{name}.npz"), **save)
+        print("nn", name, save["act_mode"].shape, save["vh"].shape, save["vl"].shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     for name, spec in CASES.items():
         run_case(name, *spec)
     run_gae()
+    run_nn()
