@@ -57,11 +57,11 @@ __device__ __forceinline__ void gemm_ws(const float* A1, int k_lo, int k_hi, con
     const int rgb = bi % NRGB, cgb = bi / NRGB;
     const int rg = rgb * 8 + (lane & 7), cg = cgb * 4 + (lane >> 3);
     if (cg >= N4) continue;
-    float acc[RT][4];
+    // packed FP32 FMA (FFMA2): accumulators are (col 2q, col 2q+1) pairs, the W float4 supplies the
+    // pairs directly and only the RT row values are duplicated
+    float2 acc2[RT][2];
 #pragma unroll
-    for (int i = 0; i < RT; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < RT; ++i) { acc2[i][0] = make_float2(0.f, 0.f); acc2[i][1] = make_float2(0.f, 0.f); }
     auto run = [&](const float* A, int ka, int kb, const float* W, int ld) {
       const float* ap = A + rg * RT;
       const float* wp = W + cg * 4;
@@ -76,21 +76,38 @@ __device__ __forceinline__ void gemm_ws(const float* A1, int k_lo, int k_hi, con
           av[0] = a.x; av[1] = a.y;
         }
         const float4 w = *reinterpret_cast<const float4*>(wp + (size_t)k * ld);
-        const float wv[4] = {w.x, w.y, w.z, w.w};
+        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
-        for (int i = 0; i < RT; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        for (int i = 0; i < RT; ++i) {
+          const float2 ad = make_float2(av[i], av[i]);
+          acc2[i][0] = __ffma2_rn(ad, w01, acc2[i][0]);
+          acc2[i][1] = __ffma2_rn(ad, w23, acc2[i][1]);
+        }
       }
     };
     run(A1, k_lo, k_hi, W1, ld1);
+    float acc[RT][4];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      acc[i][0] = acc2[i][0].x; acc[i][1] = acc2[i][0].y; acc[i][2] = acc2[i][1].x; acc[i][3] = acc2[i][1].y;
+    }
     if (scale1 != 1.f) {
 #pragma unroll
       for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] *= scale1;
     }
-    if (K2 > 0) run(A2, 0, K2, W2, ld2);
+    if (K2 > 0) {
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        acc2[i][0] = make_float2(acc[i][0], acc[i][1]); acc2[i][1] = make_float2(acc[i][2], acc[i][3]);
+      }
+      run(A2, 0, K2, W2, ld2);
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        acc[i][0] = acc2[i][0].x; acc[i][1] = acc2[i][0].y; acc[i][2] = acc2[i][1].x; acc[i][3] = acc2[i][1].y;
+      }
+    }
     epi(rg * RT, cg * 4, acc);
   }
 }
@@ -434,24 +451,32 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
 // conflict-free LDS.32 per column: 4-6 FFMA per shared-memory wavefront, and no
 // block-wide barrier inside the tile loop (warps never exchange data).
 
-// out[c][r0..r0+7] = bias[c] + sum_k A[k][r0..r0+7] * W[k][c]   for c = lane, lane + 32
+// out[c][r0..r0+WR) = bias[c] + sum_k A[k][r0..r0+WR) * W[k][c]   for c = lane, lane + 32.
+// Packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2, new on sm_100): accumulators are (row 2p, row 2p+1)
+// pairs, the A float4 supplies the row pairs directly and only the two weights are duplicated, so
+// each k costs 2 MOV + WR FFMA2 instead of 2*WR FFMA (B200: 65.9 vs 42.4 TFLOP/s measured,
+// tools/micro/ffma2_bench.cu).  Each half is an IEEE fma: results equal scalar fmaf bit for bit.
 template <int WR>
 __device__ __forceinline__ void warp_dense64(const float* A, const float* W, const float* bias,
                                              float* out, int r0, int lane) {
-  float acc[WR][2];
+  float2 acc[WR / 2][2];
 #pragma unroll
-  for (int i = 0; i < WR; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+  for (int p = 0; p < WR / 2; ++p) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = make_float2(0.f, 0.f); }
 #pragma unroll 4
   for (int k = 0; k < HID; ++k) {
-    float av[WR];
+    float2 ap[WR / 2];
 #pragma unroll
     for (int i4 = 0; i4 < WR / 4; ++i4) {
       const float4 a = *reinterpret_cast<const float4*>(A + k * RS + r0 + 4 * i4);
-      av[4 * i4] = a.x; av[4 * i4 + 1] = a.y; av[4 * i4 + 2] = a.z; av[4 * i4 + 3] = a.w;
+      ap[2 * i4] = make_float2(a.x, a.y); ap[2 * i4 + 1] = make_float2(a.z, a.w);
     }
     const float w0 = W[k * HID + lane], w1 = W[k * HID + lane + 32];
+    const float2 w0d = make_float2(w0, w0), w1d = make_float2(w1, w1);
 #pragma unroll
-    for (int i = 0; i < WR; ++i) { acc[i][0] = fmaf(av[i], w0, acc[i][0]); acc[i][1] = fmaf(av[i], w1, acc[i][1]); }
+    for (int p = 0; p < WR / 2; ++p) {
+      acc[p][0] = __ffma2_rn(ap[p], w0d, acc[p][0]);
+      acc[p][1] = __ffma2_rn(ap[p], w1d, acc[p][1]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -460,7 +485,7 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
 #pragma unroll
     for (int i4 = 0; i4 < WR / 4; ++i4)
       *reinterpret_cast<float4*>(out + c * RS + r0 + 4 * i4) =
-          make_float4(acc[4 * i4][j] + bj, acc[4 * i4 + 1][j] + bj, acc[4 * i4 + 2][j] + bj, acc[4 * i4 + 3][j] + bj);
+          make_float4(acc[2 * i4][j].x + bj, acc[2 * i4][j].y + bj, acc[2 * i4 + 1][j].x + bj, acc[2 * i4 + 1][j].y + bj);
   }
 }
 
@@ -550,29 +575,34 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
     __syncwarp();
     // GRU cell (flax GRUCell; rnn.py:19-21): 8 rows x units {lane, lane+32} x 3 gates
     {
-      float ai[3][WR][2], ah[3][WR][2];
+      float2 ai[3][WR / 2][2], ah[3][WR / 2][2];      // (row 2p, row 2p+1) pairs, see warp_dense64
 #pragma unroll
       for (int t = 0; t < 3; ++t)
 #pragma unroll
-        for (int i = 0; i < WR; ++i) { ai[t][i][0] = ai[t][i][1] = 0.f; ah[t][i][0] = ah[t][i][1] = 0.f; }
+        for (int p = 0; p < WR / 2; ++p) {
+          ai[t][p][0] = ai[t][p][1] = make_float2(0.f, 0.f);
+          ah[t][p][0] = ah[t][p][1] = make_float2(0.f, 0.f);
+        }
 #pragma unroll 2
       for (int k = 0; k < HID; ++k) {
-        float xv[WR], hv[WR];
+        float2 xp[WR / 2], hp[WR / 2];
 #pragma unroll
         for (int i4 = 0; i4 < WR / 4; ++i4) {
           const float4 xa = *reinterpret_cast<const float4*>(y0 + k * RS + r0 + 4 * i4);
           const float4 ha = *reinterpret_cast<const float4*>(hbuf + k * RS + r0 + 4 * i4);
-          xv[4 * i4] = xa.x; xv[4 * i4 + 1] = xa.y; xv[4 * i4 + 2] = xa.z; xv[4 * i4 + 3] = xa.w;
-          hv[4 * i4] = ha.x; hv[4 * i4 + 1] = ha.y; hv[4 * i4 + 2] = ha.z; hv[4 * i4 + 3] = ha.w;
+          xp[2 * i4] = make_float2(xa.x, xa.y); xp[2 * i4 + 1] = make_float2(xa.z, xa.w);
+          hp[2 * i4] = make_float2(ha.x, ha.y); hp[2 * i4 + 1] = make_float2(ha.z, ha.w);
         }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
           const float wi0 = wi[k * 192 + t * 64 + lane], wi1 = wi[k * 192 + t * 64 + lane + 32];
           const float wh0 = wh[k * 192 + t * 64 + lane], wh1 = wh[k * 192 + t * 64 + lane + 32];
+          const float2 wi0d = make_float2(wi0, wi0), wi1d = make_float2(wi1, wi1);
+          const float2 wh0d = make_float2(wh0, wh0), wh1d = make_float2(wh1, wh1);
 #pragma unroll
-          for (int i = 0; i < WR; ++i) {
-            ai[t][i][0] = fmaf(xv[i], wi0, ai[t][i][0]); ai[t][i][1] = fmaf(xv[i], wi1, ai[t][i][1]);
-            ah[t][i][0] = fmaf(hv[i], wh0, ah[t][i][0]); ah[t][i][1] = fmaf(hv[i], wh1, ah[t][i][1]);
+          for (int p = 0; p < WR / 2; ++p) {
+            ai[t][p][0] = __ffma2_rn(xp[p], wi0d, ai[t][p][0]); ai[t][p][1] = __ffma2_rn(xp[p], wi1d, ai[t][p][1]);
+            ah[t][p][0] = __ffma2_rn(hp[p], wh0d, ah[t][p][0]); ah[t][p][1] = __ffma2_rn(hp[p], wh1d, ah[t][p][1]);
           }
         }
       }
@@ -583,10 +613,14 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
         float hn[WR];
 #pragma unroll
         for (int i = 0; i < WR; ++i) {
+          const int p = i >> 1;
+          const float air = (i & 1) ? ai[0][p][j].y : ai[0][p][j].x, ahr = (i & 1) ? ah[0][p][j].y : ah[0][p][j].x;
+          const float aiz = (i & 1) ? ai[1][p][j].y : ai[1][p][j].x, ahz = (i & 1) ? ah[1][p][j].y : ah[1][p][j].x;
+          const float ain = (i & 1) ? ai[2][p][j].y : ai[2][p][j].x, ahn = (i & 1) ? ah[2][p][j].y : ah[2][p][j].x;
           const float hprev = hbuf[c * RS + r0 + i];
-          const float rgate = sigmoidf_(ai[0][i][j] + bir + ah[0][i][j]);
-          const float zgate = sigmoidf_(ai[1][i][j] + biz + ah[1][i][j]);
-          const float cand = tanhf(ai[2][i][j] + bin + rgate * (ah[2][i][j] + bh));
+          const float rgate = sigmoidf_(air + bir + ahr);
+          const float zgate = sigmoidf_(aiz + biz + ahz);
+          const float cand = tanhf(ain + bin + rgate * (ahn + bh));
           hn[i] = (1.f - zgate) * cand + zgate * hprev;
         }
 #pragma unroll
