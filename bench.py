@@ -284,6 +284,13 @@ def run_gpu(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # the same through the full public call: algo.collect(params, keys) = device-side reset (K0 rejection
+    # sampler) + LiDAR + graph + rollout.  Reported beside the metric; the metric itself uses synthetic states.
+    keys = np.arange(b, dtype=np.uint64) + 7919 * (rank + 1)
+    algo.collect(algo.params, keys, record=record)
+    ms_api = timed(lambda: algo.collect(algo.params, keys, record=record), max(1, args.steps // 2))
+    ms_api /= max(1, args.steps // 2)
+
     units = b * T * n * world
     value = units * args.steps / (ms * 1e-3)
     e2e = units * args.steps / (ms_e2e * 1e-3)
@@ -315,6 +322,7 @@ def run_gpu(args):
                                  "see DESIGN.md for the compute roofline"},
             "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof),
             "rollout_streams": algo.rollout_chunks,
+            "api_collect_with_reset": {"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT},
             "rollout_hbm": {"unique_record_bytes_per_env_step": rec_bytes, "achieved_gbs": rollout_gbs,
                             "frac_of_hbm": rollout_gbs / hbm},
         }

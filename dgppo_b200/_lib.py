@@ -56,6 +56,8 @@ OBS_STRIDE = 16
 SIGNATURES = {
     "dgppo_abi_version": (C.c_int, []),
     "dgppo_graph_dims": (C.c_int, [C.POINTER(DgppoEnvCfg), C.POINTER(DgppoGraphDims)]),
+    "dgppo_reset": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), _fp, C.c_double, C.c_double, C.c_double, C.c_double,
+                              _fp, _fp, _fp, _fp, C.c_int32]),
     "dgppo_env_step": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                  C.c_int32, C.c_int32]),
     "dgppo_lidar": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), _fp, _fp, _fp, _fp, C.c_int32]),

@@ -1,0 +1,199 @@
+// Device-side env.reset: obstacle sampling + the rejection sampler of
+// get_node_goal_rng (dgppo/env/utils.py:139-244) for LidarEnv.reset
+// (lidar_env/base.py:89-124), LidarBicycleTarget.reset
+// (lidar_bicycle_target.py:60-90) and MPE.reset (mpe/base.py:81-127).
+//
+// One warp per environment: the sampler is sequential per env (agent by agent,
+// candidate by candidate), the validity test of a candidate (distance to the
+// nodes placed so far, inside-obstacle test) is lane-parallel.
+//
+// Random numbers: jax's threefry streams cannot be reproduced (and need not be:
+// only the accept / reject rules are semantics).  Draw `c` of env key `k` is the
+// counter-based hash splitmix64(k + c * golden) -> two 24-bit uniforms; the
+// oracle (oracle/reset_np.py) uses the same function, so kernel and oracle place
+// identical agents / goals / obstacles for identical keys.
+#include "common.cuh"
+
+namespace dgppo {
+
+struct ResetConsts {
+  int kind, n, n_obs;
+  float area, min_dist, car, obs_r, len_lo, len_hi, th_lo, th_hi;
+};
+
+__host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+  x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+  x ^= x >> 31;
+  return x;
+}
+
+struct Rng {
+  unsigned long long key; unsigned ctr;
+  __device__ __forceinline__ float2 next2() {          // two uniforms in [0, 1)
+    const unsigned long long x = splitmix64(key + (unsigned long long)(ctr++) * 0x9E3779B97F4A7C15ULL);
+    return make_float2((float)(x >> 40) * (1.f / 16777216.f), (float)((x >> 8) & 0xFFFFFFu) * (1.f / 16777216.f));
+  }
+};
+
+// Rectangle.inside with margin r (obstacle.py:62-72), any obstacle; lane-parallel over obstacles
+__device__ __forceinline__ bool inside_any(float px, float py, const float* rec, int n_obs, float r, int lane) {
+  bool in = false;
+  for (int o = lane; o < n_obs; o += 32) {
+    const float* q = rec + o * DGPPO_OBS_STRIDE;
+    const float rel_x = fsub(px, q[0]), rel_y = fsub(py, q[1]);
+    const float cs = q[5], sn = q[6];
+    const float xx = fsub(fabsf(fadd(fmul(rel_x, cs), fmul(rel_y, sn))), fdiv(q[2], 2.f));
+    const float yy = fsub(fabsf(fsub(fmul(rel_x, sn), fmul(rel_y, cs))), fdiv(q[3], 2.f));
+    const bool in_down = (xx < r) && (yy < 0.f), in_up = (xx < 0.f) && (yy < r);
+    const bool corner = (xx > 0.f) && (yy > 0.f) && (fsqrt(fadd(fmul(xx, xx), fmul(yy, yy))) < r);
+    in |= in_down || in_up || corner;
+  }
+  return __any_sync(0xffffffffu, in);
+}
+
+// min_j |p_j - cand| <= min_dist over ALL n slots (unplaced slots sit at the origin, as the
+// reference's zero-initialised all_nodes do: env/utils.py:151-152,171)
+__device__ __forceinline__ bool collides(float cx, float cy, const float* pts, int n, float min_dist, int lane) {
+  bool hit = false;
+  for (int j = lane; j < n; j += 32) hit |= norm2(fsub(pts[2 * j], cx), fsub(pts[2 * j + 1], cy)) <= min_dist;
+  return __any_sync(0xffffffffu, hit);
+}
+
+constexpr int RESET_WARPS = 4;
+constexpr int RESET_MAX_ITER = 1024;           // env/utils.py:150
+
+__global__ void __launch_bounds__(RESET_WARPS * 32)
+reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* __restrict__ agent,
+             float* __restrict__ goal, float* __restrict__ obst, int* __restrict__ n_draws, int b, int sd) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * RESET_WARPS + warp;
+  if (env >= b) return;
+  const int n = k.n;
+  const bool lid = is_lidar(k.kind);
+  float* st = smem + (size_t)warp * (4 * n + k.n_obs * DGPPO_OBS_STRIDE);   // agent xy [n][2]
+  float* gl = st + 2 * n;                                                    // goal xy  [n][2]
+  float* rec = gl + 2 * n;                                                   // obstacle records (Lidar)
+  Rng rng{keys[env], 0u};
+
+  // ---- obstacles (Lidar): centre, (width, height), theta -> Rectangle.create (obstacle.py:39-56)
+  if (lid) {
+    for (int o = 0; o < k.n_obs; ++o) {
+      const float2 c = rng.next2(), l = rng.next2(), t = rng.next2();
+      if (lane == 0) {
+        float* q = rec + o * DGPPO_OBS_STRIDE;
+        const float cx = fmul(c.x, k.area), cy = fmul(c.y, k.area);
+        const float w = fadd(k.len_lo, fmul(l.x, fsub(k.len_hi, k.len_lo)));
+        const float h = fadd(k.len_lo, fmul(l.y, fsub(k.len_hi, k.len_lo)));
+        const float th = fadd(k.th_lo, fmul(t.x, fsub(k.th_hi, k.th_lo)));
+        const float cs = cosf(th), sn = sinf(th), hw = fdiv(w, 2.f), hh = fdiv(h, 2.f);
+        q[0] = cx; q[1] = cy; q[2] = w; q[3] = h; q[4] = th; q[5] = cs; q[6] = sn; q[7] = 0.f;
+        const float bx[4] = {hw, -hw, -hw, hw}, by[4] = {hh, hh, -hh, -hh};
+        for (int p = 0; p < 4; ++p) {
+          q[8 + 2 * p] = fadd(fadd(fmul(cs, bx[p]), fmul(-sn, by[p])), cx);
+          q[9 + 2 * p] = fadd(fadd(fmul(sn, bx[p]), fmul(cs, by[p])), cy);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  const float* recp = lid ? rec : nullptr;
+  const int n_rect = lid ? k.n_obs : 0;
+  const float half = fdiv(k.min_dist, 2.f);
+
+  // ---- get_node_goal_rng (env/utils.py:139-244)
+  for (int j = lane; j < 2 * n; j += 32) { st[j] = 0.f; gl[j] = 0.f; }
+  __syncwarp();
+  int agent_id = 0;
+  while (agent_id < n) {
+    // agent candidate: redraw while it collides / lies in an obstacle, at most max_iter times
+    float2 u = rng.next2();
+    float cx = fmul(u.x, k.area), cy = fmul(u.y, k.area);
+    int it_a = 0;
+    while (it_a < RESET_MAX_ITER &&
+           (collides(cx, cy, st, n, k.min_dist, lane) || (n_rect > 0 && inside_any(cx, cy, recp, n_rect, half, lane)))) {
+      ++it_a; u = rng.next2(); cx = fmul(u.x, k.area); cy = fmul(u.y, k.area);
+    }
+    __syncwarp();
+    if (lane == 0) { st[2 * agent_id] = cx; st[2 * agent_id + 1] = cy; }
+    __syncwarp();
+    u = rng.next2();
+    float gx = fmul(u.x, k.area), gy = fmul(u.y, k.area);
+    int it_g = 0;
+    while (it_g < RESET_MAX_ITER &&
+           (collides(gx, gy, gl, n, k.min_dist, lane) || (n_rect > 0 && inside_any(gx, gy, recp, n_rect, half, lane)) ||
+            gx < 0.f || gy < 0.f || gx > k.area || gy > k.area)) {
+      ++it_g; u = rng.next2(); gx = fmul(u.x, k.area); gy = fmul(u.y, k.area);
+    }
+    __syncwarp();
+    if (lane == 0) { gl[2 * agent_id] = gx; gl[2 * agent_id + 1] = gy; }
+    __syncwarp();
+    ++agent_id;
+    if (it_a >= RESET_MAX_ITER || it_g >= RESET_MAX_ITER) {      // no solution found: start over (utils.py:229-232)
+      agent_id = 0;
+      for (int j = lane; j < 2 * n; j += 32) { st[j] = 0.f; gl[j] = 0.f; }
+      __syncwarp();
+    }
+  }
+
+  // ---- MPE obstacles (mpe/base.py:93-118): first candidate in [0, area]^2, redraws in [3r, area-3r]^2
+  float* oo = obst + (size_t)env * k.n_obs * (lid ? DGPPO_OBS_STRIDE : 4);
+  if (!lid) {
+    const float lo = fmul(k.car, 3.f), hi = fsub(k.area, fmul(k.car, 3.f));
+    for (int o = 0; o < k.n_obs; ++o) {
+      float2 u = rng.next2();
+      float ox = fmul(u.x, k.area), oy = fmul(u.y, k.area);
+      int guard = 0;
+      while (guard < (1 << 20) &&
+             (collides(ox, oy, st, n, fadd(k.car, k.obs_r), lane) ||
+              collides(ox, oy, gl, n, fadd(fmul(k.car, 2.f), k.obs_r), lane) ||
+              ox < lo || oy < lo || ox > hi || oy > hi)) {
+        ++guard; u = rng.next2();
+        ox = fadd(lo, fmul(u.x, fsub(hi, lo))); oy = fadd(lo, fmul(u.y, fsub(hi, lo)));
+      }
+      if (lane == 0) { oo[4 * o] = ox; oo[4 * o + 1] = oy; oo[4 * o + 2] = 0.f; oo[4 * o + 3] = 0.f; }
+    }
+  } else {
+    for (int j = lane; j < k.n_obs * DGPPO_OBS_STRIDE; j += 32) oo[j] = rec[j];
+  }
+
+  // ---- states: [x, y, 0, 0] or bicycle [x, y, cos th, sin th, 0] with th ~ U[0, 2 pi)
+  float* ao = agent + (size_t)env * n * sd;
+  float* go = goal + (size_t)env * n * sd;
+  for (int i = 0; i < n; ++i) {
+    float cs = 0.f, sn = 0.f;
+    if (sd == 5) { const float2 u = rng.next2(); const float th = fmul(u.x, 6.283185307179586f); cs = cosf(th); sn = sinf(th); }
+    if (lane == 0) {
+      ao[i * sd] = st[2 * i]; ao[i * sd + 1] = st[2 * i + 1];
+      go[i * sd] = gl[2 * i]; go[i * sd + 1] = gl[2 * i + 1];
+      for (int c = 2; c < sd; ++c) { ao[i * sd + c] = 0.f; go[i * sd + c] = 0.f; }
+      if (sd == 5) { ao[i * sd + 2] = cs; ao[i * sd + 3] = sn; }
+    }
+  }
+  if (n_draws && lane == 0) n_draws[env] = (int)rng.ctr;
+}
+
+}  // namespace dgppo
+
+using namespace dgppo;
+
+extern "C" int dgppo_reset(void* stream, const DgppoEnvCfg* cfg, const uint64_t* keys,
+                           double obs_len_lo, double obs_len_hi, double theta_lo, double theta_hi,
+                           float* agent, float* goal, float* obstacles, int32_t* n_draws, int32_t b) {
+  if (int rc = check_env_cfg(cfg)) return rc;
+  if (b == 0) return 0;
+  if (b < 0 || !keys || !agent || !goal || (cfg->n_obs > 0 && !obstacles)) return DGPPO_EINVAL;
+  ResetConsts k;
+  k.kind = cfg->kind; k.n = cfg->n_agents; k.n_obs = cfg->n_obs;
+  k.area = (float)cfg->area_size;
+  k.min_dist = (float)((is_lidar(cfg->kind) ? 2.2 : 2.0) * cfg->car_radius);   // lidar_env/base.py:111 | mpe/base.py:88
+  k.car = (float)cfg->car_radius; k.obs_r = (float)cfg->obs_radius;
+  k.len_lo = (float)obs_len_lo; k.len_hi = (float)obs_len_hi; k.th_lo = (float)theta_lo; k.th_hi = (float)theta_hi;
+  const size_t smem = (size_t)RESET_WARPS * (4 * k.n + k.n_obs * DGPPO_OBS_STRIDE) * sizeof(float);
+  if (smem > 48 * 1024) return DGPPO_ENOTSUP;
+  const int grid = (b + RESET_WARPS - 1) / RESET_WARPS;
+  reset_kernel<<<grid, RESET_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      k, (const unsigned long long*)keys, agent, goal, obstacles, n_draws, b, is_bicycle(cfg->kind) ? 5 : 4);
+  return (int)cudaGetLastError();
+}

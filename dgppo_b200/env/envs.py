@@ -4,8 +4,8 @@ Mirrors dgppo/env/lidar_env/{base,lidar_spread,lidar_target,
 lidar_bicycle_target}.py and dgppo/env/mpe/{base,mpe_spread}.py: same class
 names, PARAMS, dims, `reset / step / get_graph / get_cost / get_lidar_data /
 agent_step_euler / state_lim / action_lim`.  The arithmetic of step, LiDAR and
-graph construction runs in libdgppo_b200.so (K1/K2/K3); `reset`'s rejection
-sampling (env/utils.py:139-244) is host-side NumPy for now.
+graph construction runs in libdgppo_b200.so (K1/K2/K3), and so does `reset`'s
+obstacle sampling + rejection sampler (K0 `dgppo_reset`; env/utils.py:139-244).
 """
 from __future__ import annotations
 
@@ -71,62 +71,6 @@ def rect_record(center, width, height, theta) -> np.ndarray:
     return rec
 
 
-def _rect_inside_np(pos: np.ndarray, rec: np.ndarray, r: float) -> np.ndarray:
-    """inside_obstacles (env/utils.py:82-112, obstacle.py:62-72): pos (b,2),
-    rec (b,o,16) -> (b,) bool.  Host-side, used by reset only."""
-    rel_x = pos[:, None, 0] - rec[..., 0]
-    rel_y = pos[:, None, 1] - rec[..., 1]
-    c, s = rec[..., 5], rec[..., 6]
-    xx = np.abs(rel_x * c + rel_y * s) - rec[..., 2] / 2
-    yy = np.abs(rel_x * s - rel_y * c) - rec[..., 3] / 2
-    is_in = ((xx < r) & (yy < 0)) | ((xx < 0) & (yy < r)) | ((xx > 0) & (yy > 0) & (np.sqrt(xx ** 2 + yy ** 2) < r))
-    return is_in.any(axis=-1)
-
-
-def _node_goal_rng(rng: np.random.Generator, b: int, side: float, n: int, min_dist: float,
-                   rec: Optional[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
-    """get_node_goal_rng (env/utils.py:139-244), vectorised over b envs: agents
-    and goals are placed one at a time by rejection sampling (<= 1024 tries
-    each; a failure restarts that env from agent 0).  Unplaced slots sit at the
-    origin and repel candidates, as in the reference (zeros-initialised
-    `all_nodes`).  The PRNG stream is NumPy's, not jax.random's."""
-    max_iter = 1024
-    states = np.zeros((b, n, 2), F)
-    goals = np.zeros((b, n, 2), F)
-    agent_id = np.zeros(b, np.int64)
-    rows = np.arange(b)
-
-    def place(existing, extra_check):
-        cand = rng.uniform(0, side, (b, 2)).astype(F)
-        n_iter = np.zeros(b, np.int64)
-        while True:
-            dmin = np.linalg.norm(existing - cand[:, None, :], axis=-1).min(axis=1)
-            bad = dmin <= min_dist
-            if rec is not None:
-                bad |= _rect_inside_np(cand, rec, min_dist / 2)
-            bad |= extra_check(cand)
-            bad &= n_iter < max_iter
-            if not bad.any():
-                return cand, n_iter
-            cand = np.where(bad[:, None], rng.uniform(0, side, (b, 2)).astype(F), cand)
-            n_iter += bad
-    while (agent_id < n).any():
-        act = agent_id < n
-        idx = np.minimum(agent_id, n - 1)
-        a_c, it_a = place(states, lambda c: np.zeros(b, bool))
-        new_states = states.copy()
-        new_states[rows, idx] = a_c
-        g_c, it_g = place(goals, lambda c: (c < 0).any(axis=1) | (c > side).any(axis=1))
-        new_goals = goals.copy()
-        new_goals[rows, idx] = g_c
-        ok = (it_a < max_iter) & (it_g < max_iter)
-        upd = act[:, None, None]
-        states = np.where(upd, np.where(ok[:, None, None], new_states, 0), states).astype(F)
-        goals = np.where(upd, np.where(ok[:, None, None], new_goals, 0), goals).astype(F)
-        agent_id = np.where(act, np.where(ok, agent_id + 1, 0), agent_id)
-    return states, goals
-
-
 def _as_seeds(key) -> Tuple[np.ndarray, bool]:
     """`key` may be an int, a sequence / array of ints (one env per entry), or
     a (b, 2) uint32 array shaped like a batch of jax PRNG keys."""
@@ -138,6 +82,23 @@ def _as_seeds(key) -> Tuple[np.ndarray, bool]:
     if k.ndim == 2:
         k = (k[:, 0].astype(np.uint64) << np.uint64(32)) | k[:, 1].astype(np.uint64)
     return k.astype(np.uint64), False
+
+
+def _reset_kernel(env, seeds: np.ndarray, dev, obs_len=(0.0, 0.0), theta=(0.0, 0.0)):
+    """K0: sample obstacles / agents / goals for len(seeds) environments on the device."""
+    b, n, sd = len(seeds), env.num_agents, env.state_dim
+    n_obs = int(env.params.get("n_obs", 0))
+    lidar = isinstance(env, LidarEnv)
+    keys = torch.from_numpy(seeds.astype(np.int64)).to(dev)           # same 64 bits, signed container
+    agent = torch.empty((b, n, sd), dtype=torch.float32, device=dev)
+    goal = torch.empty((b, n, sd), dtype=torch.float32, device=dev)
+    obst = torch.empty((b, n_obs, _lib.OBS_STRIDE if lidar else 4), dtype=torch.float32, device=dev) \
+        if n_obs > 0 else None
+    cfg = env.env_cfg()
+    _lib.check(_lib.lib().dgppo_reset(stream_ptr(), C.byref(cfg), ptr(keys), float(obs_len[0]), float(obs_len[1]),
+                                       float(theta[0]), float(theta[1]), ptr(agent), ptr(goal), ptr(obst), None, b),
+               "dgppo_reset")
+    return agent, goal, obst
 
 
 def _batchify(*ts):
@@ -262,28 +223,14 @@ class LidarEnv(_KernelEnv):
             self._rays = dev_f32(tab, device)
         return self._rays
 
-    def _extra_agent_state(self, rng, b):
-        return np.zeros((b, self.num_agents, self.state_dim - 2), F)
-
     def reset(self, key) -> GraphsTuple:
+        """LidarEnv.reset (lidar_env/base.py:89-124): sampling on the device (K0), then LiDAR + graph."""
         dev = require_cuda()
         seeds, single = _as_seeds(key)
-        b, n = len(seeds), self.num_agents
-        rng = np.random.default_rng(seeds)
-        n_obs = self._params["n_obs"]
-        assert n_obs >= 0
-        rec = None
-        if n_obs > 0:
-            pos = rng.uniform(0, self.area_size, (b, n_obs, 2)).astype(F)
-            lo, hi = self._params["obs_len_range"]
-            ln = rng.uniform(lo, hi, (b, n_obs, 2)).astype(F)
-            th = rng.uniform(self._OBS_THETA[0], self._OBS_THETA[1], (b, n_obs)).astype(F)
-            rec = rect_record(pos, ln[..., 0], ln[..., 1], th)
-        states, goals = _node_goal_rng(rng, b, self.area_size, n, 2.2 * self._params["car_radius"], rec)
-        agent = np.concatenate([states, self._extra_agent_state(rng, b)], axis=-1).astype(F)
-        goal = np.concatenate([goals, np.zeros((b, n, self.state_dim - 2), F)], axis=-1)
+        assert self._params["n_obs"] >= 0
+        agent, goal, rec = _reset_kernel(self, seeds, dev, self._params["obs_len_range"], self._OBS_THETA)
         obstacles = Rectangle.from_record(rec, dev) if rec is not None else None
-        env_state = LidarEnvState(dev_f32(agent, dev), dev_f32(goal, dev), obstacles)
+        env_state = LidarEnvState(agent, goal, obstacles)
         lidar = self.get_lidar_data(env_state.agent, obstacles)
         g = self.get_graph(env_state, lidar)
         if single:
@@ -415,10 +362,6 @@ class LidarBicycleTarget(LidarTarget):
     def node_dim(self) -> int:
         return 8
 
-    def _extra_agent_state(self, rng, b):
-        th = rng.uniform(0, 2 * np.pi, (b, self.num_agents)).astype(F)
-        return np.stack([np.cos(th), np.sin(th), np.zeros_like(th)], axis=-1).astype(F)
-
     def state_lim(self, state=None):
         A = self.area_size
         return torch.tensor([0., 0., -1., -1., -0.5]), torch.tensor([A, A, 1., 1., 0.5])
@@ -455,33 +398,14 @@ class MPE(_KernelEnv):
         return 7
 
     def reset(self, key) -> GraphsTuple:
-        """MPE.reset (mpe/base.py:81-127); host-side sampling."""
+        """MPE.reset (mpe/base.py:81-127): sampling on the device (K0), then the graph."""
         dev = require_cuda()
         seeds, single = _as_seeds(key)
-        b, n = len(seeds), self.num_agents
-        rng = np.random.default_rng(seeds)
-        p = self._params
-        states, goals = _node_goal_rng(rng, b, self.area_size, n, 2 * p["car_radius"], None)
-        n_obs = p["n_obs"]
-        obs = np.zeros((b, n_obs, 2), F)
-        lo, hi = p["car_radius"] * 3, self.area_size - p["car_radius"] * 3
-        for o in range(n_obs):
-            cand = rng.uniform(0, self.area_size, (b, 2)).astype(F)
-            while True:
-                da = np.linalg.norm(states - cand[:, None], axis=-1).min(axis=1)
-                dg = np.linalg.norm(goals - cand[:, None], axis=-1).min(axis=1)
-                bad = (da <= p["car_radius"] + p["obs_radius"]) | (dg <= p["car_radius"] * 2 + p["obs_radius"]) | \
-                      (cand < lo).any(axis=1) | (cand > hi).any(axis=1)
-                if not bad.any():
-                    break
-                cand = np.where(bad[:, None], rng.uniform(lo, hi, (b, 2)).astype(F), cand)
-            obs[:, o] = cand
-        z = lambda x: np.concatenate([x, np.zeros_like(x)], axis=-1)
-        env_state = MPEEnvState(dev_f32(z(states), dev), dev_f32(z(goals), dev),
-                                dev_f32(z(obs), dev) if n_obs > 0 else None)
+        agent, goal, obs = _reset_kernel(self, seeds, dev)
+        env_state = MPEEnvState(agent, goal, obs)
         g = self.get_graph(env_state)
         if single:
-            es = MPEEnvState(env_state.agent[0], env_state.goal[0], None if n_obs == 0 else env_state.obs[0])
+            es = MPEEnvState(agent[0], goal[0], None if obs is None else obs[0])
             return self._squeeze_graph(g, es)
         return g
 

@@ -88,6 +88,24 @@ int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out);
  * cos/sin are carried as data (obstacle.py:65-66 re-evaluates them per call). */
 #define DGPPO_OBS_STRIDE 16
 
+/* ---- K0: reset (sampling part) ----------------------------------------------
+ * The random part of LidarEnv.reset / LidarBicycleTarget.reset / MPE.reset
+ * (lidar_env/base.py:89-119, lidar_bicycle_target.py:60-85, mpe/base.py:81-125):
+ * obstacle sampling + Rectangle.create (obstacle.py:39-56) and the rejection
+ * sampler get_node_goal_rng (env/utils.py:139-244: <= 1024 tries per agent / goal,
+ * restart from agent 0 on failure, unplaced slots repel from the origin).  The
+ * caller then runs dgppo_lidar + dgppo_build_graph on the result, as reset does.
+ *   keys      (b) u64 : one key per environment; draw c of key k is
+ *             splitmix64(k + c * 0x9E3779B97F4A7C15) -> two 24-bit uniforms (jax's
+ *             threefry streams are not reproduced; the accept / reject rules are)
+ *   obs_len_lo/hi, theta_lo/hi : PARAMS["obs_len_range"], obstacle angle range
+ *             ([0, 2 pi) LidarEnv, [-pi, pi) bicycle); ignored for MPE
+ *   agent, goal (b, n, state_dim) out; obstacles (b, n_obs, DGPPO_OBS_STRIDE) out
+ *             (Lidar) or (b, n_obs, 4) out (MPE); n_draws (b) out, nullable.        */
+int dgppo_reset(void* stream, const DgppoEnvCfg* cfg, const uint64_t* keys,
+                double obs_len_lo, double obs_len_hi, double theta_lo, double theta_hi,
+                float* agent, float* goal, float* obstacles, int32_t* n_draws, int32_t b);
+
 /* ---- K1: dynamics + reward + cost ------------------------------------
  * Replaces the arithmetic of LidarEnv.step / MPE.step minus LiDAR and graph
  * build: clip_action + agent_step_euler + clip_state

@@ -1,0 +1,119 @@
+"""NumPy restatement of the reset sampler: obstacle sampling + get_node_goal_rng
+(dgppo/env/utils.py:139-244, lidar_env/base.py:89-119, mpe/base.py:81-125,
+lidar_bicycle_target.py:60-85) on the counter-based hash stream that
+dgppo_reset uses (include/dgppo_abi.h, K0).  TEST INFRASTRUCTURE: a plain
+per-environment Python loop, for small batches.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import env_np
+
+F = np.float32
+MASK = (1 << 64) - 1
+MAX_ITER = 1024
+
+
+def splitmix64(x: int) -> int:
+    x &= MASK
+    x ^= x >> 30; x = (x * 0xBF58476D1CE4E5B9) & MASK
+    x ^= x >> 27; x = (x * 0x94D049BB133111EB) & MASK
+    x ^= x >> 31
+    return x
+
+
+class Rng:
+    def __init__(self, key: int):
+        self.key, self.ctr = int(key) & MASK, 0
+
+    def next2(self):
+        x = splitmix64(self.key + self.ctr * 0x9E3779B97F4A7C15)
+        self.ctr += 1
+        s = F(1.0 / 16777216.0)
+        return F(x >> 40) * s, F((x >> 8) & 0xFFFFFF) * s
+
+
+def _inside_any(p, rec, r):
+    if rec is None or len(rec) == 0:
+        return False
+    obs = dict(center=rec[None, :, 0:2], width=rec[None, :, 2], height=rec[None, :, 3], cos=rec[None, :, 5],
+               sin=rec[None, :, 6])
+    return bool(env_np.rect_inside(np.asarray(p, F)[None, None, :], obs, r)[0, 0])
+
+
+def _collides(c, pts, min_dist):
+    d = env_np.norm2((pts[:, 0] - c[0]).astype(F), (pts[:, 1] - c[1]).astype(F))
+    return bool((d <= F(min_dist)).any())
+
+
+def reset_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3), theta_range=None):
+    """-> agent (n, sd), goal (n, sd), obstacle record (n_obs, 16) | mpe obs (n_obs, 4) | None, n_draws"""
+    rng = Rng(key)
+    n, A = cfg.n, F(cfg.area)
+    lid = cfg.is_lidar
+    rec = None
+    if lid and cfg.n_obs > 0:
+        th_lo, th_hi = theta_range if theta_range is not None else \
+            ((-np.pi, np.pi) if cfg.is_bicycle else (0.0, 2 * np.pi))
+        lo, hi, tl, thh = F(obs_len[0]), F(obs_len[1]), F(th_lo), F(th_hi)
+        rec = np.zeros((cfg.n_obs, 16), F)
+        for o in range(cfg.n_obs):
+            c, l, t = rng.next2(), rng.next2(), rng.next2()
+            cx, cy = F(c[0] * A), F(c[1] * A)
+            w = F(lo + F(l[0] * F(hi - lo)))
+            h = F(lo + F(l[1] * F(hi - lo)))
+            th = F(tl + F(t[0] * F(thh - tl)))
+            r = env_np.rect_create(np.array([cx, cy], F), w, h, th)
+            rec[o, 0:2] = [cx, cy]
+            rec[o, 2:7] = [w, h, th, r["cos"], r["sin"]]
+            rec[o, 8:16] = r["points"].reshape(8)
+    min_dist = F((2.2 if lid else 2.0) * cfg.car_radius)
+    half = F(min_dist / F(2))
+    st, gl = np.zeros((n, 2), F), np.zeros((n, 2), F)
+    agent_id = 0
+    while agent_id < n:
+        u = rng.next2()
+        c = (F(u[0] * A), F(u[1] * A))
+        it_a = 0
+        while it_a < MAX_ITER and (_collides(c, st, min_dist) or _inside_any(c, rec, half)):
+            it_a += 1
+            u = rng.next2()
+            c = (F(u[0] * A), F(u[1] * A))
+        st[agent_id] = c
+        u = rng.next2()
+        g = (F(u[0] * A), F(u[1] * A))
+        it_g = 0
+        while it_g < MAX_ITER and (_collides(g, gl, min_dist) or _inside_any(g, rec, half)
+                                   or g[0] < 0 or g[1] < 0 or g[0] > A or g[1] > A):
+            it_g += 1
+            u = rng.next2()
+            g = (F(u[0] * A), F(u[1] * A))
+        gl[agent_id] = g
+        agent_id += 1
+        if it_a >= MAX_ITER or it_g >= MAX_ITER:
+            agent_id = 0
+            st[:] = 0
+            gl[:] = 0
+    obst = rec
+    if not lid and cfg.n_obs > 0:
+        obst = np.zeros((cfg.n_obs, 4), F)
+        car, obr = F(cfg.car_radius), F(cfg.obs_radius)
+        lo, hi = F(car * F(3)), F(A - F(car * F(3)))
+        for o in range(cfg.n_obs):
+            u = rng.next2()
+            p = (F(u[0] * A), F(u[1] * A))
+            while (_collides(p, st, F(car + obr)) or _collides(p, gl, F(F(car * F(2)) + obr))
+                   or p[0] < lo or p[1] < lo or p[0] > hi or p[1] > hi):
+                u = rng.next2()
+                p = (F(lo + F(u[0] * F(hi - lo))), F(lo + F(u[1] * F(hi - lo))))
+            obst[o, 0:2] = p
+    sd = cfg.state_dim
+    agent, goal = np.zeros((n, sd), F), np.zeros((n, sd), F)
+    agent[:, :2], goal[:, :2] = st, gl
+    if cfg.is_bicycle:
+        for i in range(n):
+            u = rng.next2()
+            th = F(u[0] * F(6.283185307179586))
+            agent[i, 2], agent[i, 3] = np.cos(th), np.sin(th)
+    return agent, goal, obst, rng.ctr

@@ -1,0 +1,87 @@
+"""GPU: K0 dgppo_reset against the oracle restatement of the reset sampler (same counter-based
+random stream), and the invariants get_node_goal_rng guarantees."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from dgppo_b200 import _lib
+from oracle import env_np, reset_np
+from tests import util
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+CASES = {
+    "LidarSpread": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=8, n_obs=8),
+    "LidarTarget": env_np.EnvCfg(env_np.LIDAR_TARGET, n=5, n_obs=2),
+    "LidarBicycleTarget": env_np.EnvCfg(env_np.LIDAR_BICYCLE_TARGET, n=4, n_obs=3),
+    "MPESpread": env_np.EnvCfg(env_np.MPE_SPREAD, n=8, n_obs=3),
+    "LidarSpread_noobs": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
+    "crowded": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=24, n_obs=12),
+}
+
+
+def _run(cfg, keys):
+    b = len(keys)
+    k = torch.from_numpy(np.asarray(keys, np.uint64).astype(np.int64)).cuda()
+    agent = torch.empty((b, cfg.n, cfg.state_dim), device="cuda")
+    goal = torch.empty_like(agent)
+    w = _lib.OBS_STRIDE if cfg.is_lidar else 4
+    obst = torch.empty((b, max(cfg.n_obs, 1), w), device="cuda")
+    nd = torch.empty(b, dtype=torch.int32, device="cuda")
+    th = (-np.pi, np.pi) if cfg.is_bicycle else (0.0, 2 * np.pi)
+    cc = util.c_cfg(cfg)
+    rc = _lib.lib().dgppo_reset(util.stream(), C.byref(cc), util.p(k), 0.1, 0.3, th[0], th[1], util.p(agent),
+                                util.p(goal), util.p(obst) if cfg.n_obs > 0 else None, util.p(nd), b)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return agent.cpu().numpy(), goal.cpu().numpy(), obst.cpu().numpy()[:, :cfg.n_obs], nd.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_reset_matches_oracle(name):
+    cfg = CASES[name]
+    keys = np.array([0, 1, 2, 12345, 2 ** 40 + 7, 2 ** 63 + 11], np.uint64)
+    agent, goal, obst, nd = _run(cfg, keys)
+    for i, key in enumerate(keys):
+        ra, rg, ro, rn = reset_np.reset_states(cfg, int(key))
+        assert nd[i] == rn, f"{name} key {key}: number of draws"
+        np.testing.assert_array_equal(agent[i][:, :2], ra[:, :2])
+        np.testing.assert_array_equal(goal[i], rg)
+        if cfg.is_bicycle:
+            np.testing.assert_allclose(agent[i][:, 2:], ra[:, 2:], rtol=1e-6, atol=1e-6)   # libm cos/sin
+        if cfg.n_obs > 0:
+            if cfg.is_lidar:
+                np.testing.assert_array_equal(obst[i][:, :5], ro[:, :5])
+                np.testing.assert_allclose(obst[i][:, 5:], ro[:, 5:], rtol=1e-6, atol=1e-6)
+            else:
+                np.testing.assert_array_equal(obst[i], ro)
+
+
+@pytest.mark.parametrize("name", ["LidarSpread", "MPESpread", "crowded"])
+def test_reset_invariants_at_scale(name):
+    cfg = CASES[name]
+    b = 2048
+    agent, goal, obst, nd = _run(cfg, np.arange(b, dtype=np.uint64) * 977 + 5)
+    min_dist = F((2.2 if cfg.is_lidar else 2.0) * cfg.car_radius)
+    for pts in (agent[..., :2], goal[..., :2]):
+        d = np.linalg.norm(pts[:, :, None] - pts[:, None], axis=-1) + np.eye(cfg.n) * 10
+        assert (d > min_dist).all()
+        assert (pts >= 0).all() and (pts <= cfg.area).all()
+        assert (np.linalg.norm(pts, axis=-1) > min_dist).all()       # the origin repels (zero-initialised slots)
+    if cfg.is_lidar:
+        ob = dict(center=obst[..., 0:2], width=obst[..., 2], height=obst[..., 3], cos=obst[..., 5], sin=obst[..., 6])
+        assert not env_np.rect_inside(agent[..., :2], ob, float(min_dist) / 2).any()
+        assert not env_np.rect_inside(goal[..., :2], ob, float(min_dist) / 2).any()
+        assert (obst[..., 2:4] >= 0.1).all() and (obst[..., 2:4] <= 0.3).all()
+    else:
+        da = np.linalg.norm(obst[:, :, None, :2] - agent[:, None, :, :2], axis=-1)
+        assert (da > cfg.car_radius + cfg.obs_radius).all()
+        assert (obst[..., :2] >= 3 * cfg.car_radius - 1e-7).all()
+    assert (nd >= 2 * cfg.n).all()
+    # different keys give different layouts; the same key is reproducible
+    a2, _, _, _ = _run(cfg, np.arange(b, dtype=np.uint64) * 977 + 5)
+    np.testing.assert_array_equal(agent, a2)
+    assert len({tuple(x) for x in agent[:, 0, :2].round(6)}) > b * 0.99
