@@ -456,7 +456,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
 // pairs, the A float4 supplies the row pairs directly and only the two weights are duplicated, so
 // each k costs 2 MOV + WR FFMA2 instead of 2*WR FFMA (B200: 65.9 vs 42.4 TFLOP/s measured,
 // tools/micro/ffma2_bench.cu).  Each half is an IEEE fma: results equal scalar fmaf bit for bit.
-template <int WR>
+template <int WR, int STR = RS>
 __device__ __forceinline__ void warp_dense64(const float* A, const float* W, const float* bias,
                                              float* out, int r0, int lane) {
   float2 acc[WR / 2][2];
@@ -467,7 +467,7 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
     float2 ap[WR / 2];
 #pragma unroll
     for (int i4 = 0; i4 < WR / 4; ++i4) {
-      const float4 a = *reinterpret_cast<const float4*>(A + k * RS + r0 + 4 * i4);
+      const float4 a = *reinterpret_cast<const float4*>(A + k * STR + r0 + 4 * i4);
       ap[2 * i4] = make_float2(a.x, a.y); ap[2 * i4 + 1] = make_float2(a.z, a.w);
     }
     const float w0 = W[k * HID + lane], w1 = W[k * HID + lane + 32];
@@ -484,21 +484,21 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
     const float bj = bias[c];
 #pragma unroll
     for (int i4 = 0; i4 < WR / 4; ++i4)
-      *reinterpret_cast<float4*>(out + c * RS + r0 + 4 * i4) =
+      *reinterpret_cast<float4*>(out + c * STR + r0 + 4 * i4) =
           make_float4(acc[2 * i4][j].x + bj, acc[2 * i4][j].y + bj, acc[2 * i4 + 1][j].x + bj, acc[2 * i4 + 1][j].y + bj);
   }
 }
 
 // LayerNorm (flax: eps 1e-6, fast variance) + ReLU over the 64 features of the
 // warp's 8 rows; 4 lanes per row, features interleaved.
-template <int WR>
+template <int WR, int STR = RS>
 __device__ __forceinline__ void warp_layernorm_relu(float* y, const float* scale, const float* bias,
                                                     int r0, int lane) {
   constexpr int LPR = 32 / WR;                       // lanes per row (4 or 8)
   const int r = r0 + lane / LPR, part = lane % LPR;
   float s = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HID / LPR; ++i) { const float v = y[(i * LPR + part) * RS + r]; s += v; s2 = fmaf(v, v, s2); }
+  for (int i = 0; i < HID / LPR; ++i) { const float v = y[(i * LPR + part) * STR + r]; s += v; s2 = fmaf(v, v, s2); }
 #pragma unroll
   for (int o = 1; o < LPR; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   const float mean = s * (1.f / HID), mean2 = s2 * (1.f / HID);
@@ -507,7 +507,7 @@ __device__ __forceinline__ void warp_layernorm_relu(float* y, const float* scale
 #pragma unroll
   for (int i = 0; i < HID / LPR; ++i) {
     const int c = i * LPR + part;
-    y[c * RS + r] = fmaxf((y[c * RS + r] - mean) * (rstd * scale[c]) + bias[c], 0.f);
+    y[c * STR + r] = fmaxf((y[c * STR + r] - mean) * (rstd * scale[c]) + bias[c], 0.f);
   }
 }
 
@@ -665,6 +665,174 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
   }
 }
 
+// head_kernel_wide: 128 rows per CTA, 16 warps x 8 rows.  Compared with head_kernel<4> the weight rows
+// are amortised over twice the rows per warp (4-6 FMA per shared-memory wavefront instead of 2.7-3.4;
+// the kernel is smem-bandwidth-bound, profiles/), which 512 threads x 128 registers allow because
+//   * the r and z gates accumulate x Wi + h Wh into ONE accumulator each (they are summed anyway),
+//   * only two [64][R3S] activation buffers exist: the GRU carry is prefetched into registers at the
+//     start of the tile and parked in the buffer the second Dense has just released.
+constexpr int R3 = 128, R3S = 132, WR3 = 8;
+
+__global__ void __launch_bounds__(512, 1)
+head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;                                   // head / GRU / tail weights
+  float* b0 = ws + pl.hw_fl;                          // [64][R3S]
+  float* b1 = b0 + HID * R3S;                         // [64][R3S]
+  float* o4 = b1 + HID * R3S;                         // [4][R3S]
+  for (int i = threadIdx.x; i < pl.hw_fl / 4; i += 512) cp_async16(ws + 4 * i, params + pl.hw_off + 4 * i);
+  cp_async_wait_all();
+  __syncthreads();
+  auto wptr = [&](const float* p) { return ws + ((p - params) - pl.hw_off); };
+  const float *d0w = wptr(net.d0w), *d0b = wptr(net.d0b), *ln0s = wptr(net.ln0s), *ln0b = wptr(net.ln0b);
+  const float *d1w = wptr(net.d1w), *d1b = wptr(net.d1b), *ln1s = wptr(net.ln1s), *ln1b = wptr(net.ln1b);
+  const float *wi = wptr(net.wi), *bi = wptr(net.bi), *wh = wptr(net.wh), *bhn = wptr(net.bhn);
+  const float *out_w = wptr(net.out_w), *out_b = wptr(net.out_b);
+  const bool policy = net.kind == DGPPO_NET_POLICY;
+  const float *scale_w = policy ? wptr(net.scale_w) : nullptr, *scale_b = policy ? wptr(net.scale_b) : nullptr;
+
+  const int n = g.n;
+  const int nr = (net.kind == DGPPO_NET_VL) ? 1 : n;       // rows per graph
+  const long total_rows = (long)g.n_graphs * nr;
+  const long n_wtiles = (total_rows + WR3 - 1) / WR3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = warp * WR3;
+  auto row_off = [&](long row) {
+    const long gi = row / nr; const int i = (int)(row - gi * nr);
+    const long env = gi / g.n_slots; const int slot = (int)(gi - env * g.n_slots);
+    return (((size_t)env * g.rnn_pitch + slot) * nr + i) * HID;
+  };
+
+  for (long wt = (long)blockIdx.x * 16 + warp; wt < n_wtiles; wt += (long)gridDim.x * 16) {
+    const long row0 = wt * WR3;
+    const int rows = (int)min((long)WR3, total_rows - row0);
+    __syncwarp();
+    // embeddings (scratch rows in rnn_out) -> b0 (transposed, async); previous carry -> registers
+    float hreg[WR3][2];
+#pragma unroll
+    for (int i = 0; i < WR3; ++i) {
+      if (i < rows) {
+        const size_t off = row_off(row0 + i);
+        cp_async4(b0 + lane * R3S + r0 + i, g.rnn_out + off + lane);
+        cp_async4(b0 + (lane + 32) * R3S + r0 + i, g.rnn_out + off + lane + 32);
+        hreg[i][0] = __ldg(g.rnn_in + off + lane); hreg[i][1] = __ldg(g.rnn_in + off + lane + 32);
+      } else {
+        b0[lane * R3S + r0 + i] = 0.f; b0[(lane + 32) * R3S + r0 + i] = 0.f;
+        hreg[i][0] = 0.f; hreg[i][1] = 0.f;
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    warp_dense64<WR3, R3S>(b0, d0w, d0b, b1, r0, lane);          // head MLP (mlp.py:14-30)
+    __syncwarp();
+    warp_layernorm_relu<WR3, R3S>(b1, ln0s, ln0b, r0, lane);
+    __syncwarp();
+    warp_dense64<WR3, R3S>(b1, d1w, d1b, b0, r0, lane);
+    __syncwarp();
+    warp_layernorm_relu<WR3, R3S>(b0, ln1s, ln1b, r0, lane);
+    // park the carry (transposed) in b1, which the second Dense no longer needs
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i4 = 0; i4 < WR3 / 4; ++i4)
+        *reinterpret_cast<float4*>(b1 + (lane + 32 * j) * R3S + r0 + 4 * i4) =
+            make_float4(hreg[4 * i4][j], hreg[4 * i4 + 1][j], hreg[4 * i4 + 2][j], hreg[4 * i4 + 3][j]);
+    __syncwarp();
+    // GRU cell (flax GRUCell; rnn.py:19-21): x = b0, h = b1; units {lane, lane + 32}
+    float hn[WR3][2];
+    {
+      float2 ar[WR3 / 2][2], az[WR3 / 2][2], an[WR3 / 2][2], ahn[WR3 / 2][2];
+#pragma unroll
+      for (int p = 0; p < WR3 / 2; ++p)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) ar[p][j] = az[p][j] = an[p][j] = ahn[p][j] = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int k = 0; k < HID; ++k) {
+        float2 xp[WR3 / 2], hp[WR3 / 2];
+#pragma unroll
+        for (int i4 = 0; i4 < WR3 / 4; ++i4) {
+          const float4 xa = *reinterpret_cast<const float4*>(b0 + k * R3S + r0 + 4 * i4);
+          const float4 ha = *reinterpret_cast<const float4*>(b1 + k * R3S + r0 + 4 * i4);
+          xp[2 * i4] = make_float2(xa.x, xa.y); xp[2 * i4 + 1] = make_float2(xa.z, xa.w);
+          hp[2 * i4] = make_float2(ha.x, ha.y); hp[2 * i4 + 1] = make_float2(ha.z, ha.w);
+        }
+        const float* wik = wi + k * 192 + lane;
+        const float* whk = wh + k * 192 + lane;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float2 wir = make_float2(wik[32 * j], wik[32 * j]), whr = make_float2(whk[32 * j], whk[32 * j]);
+          const float2 wiz = make_float2(wik[64 + 32 * j], wik[64 + 32 * j]);
+          const float2 whz = make_float2(whk[64 + 32 * j], whk[64 + 32 * j]);
+          const float2 win = make_float2(wik[128 + 32 * j], wik[128 + 32 * j]);
+          const float2 whn = make_float2(whk[128 + 32 * j], whk[128 + 32 * j]);
+#pragma unroll
+          for (int p = 0; p < WR3 / 2; ++p) {
+            ar[p][j] = __ffma2_rn(xp[p], wir, ar[p][j]); ar[p][j] = __ffma2_rn(hp[p], whr, ar[p][j]);
+            az[p][j] = __ffma2_rn(xp[p], wiz, az[p][j]); az[p][j] = __ffma2_rn(hp[p], whz, az[p][j]);
+            an[p][j] = __ffma2_rn(xp[p], win, an[p][j]);
+            ahn[p][j] = __ffma2_rn(hp[p], whn, ahn[p][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = lane + 32 * j;
+        const float bir = bi[c], biz = bi[64 + c], bin = bi[128 + c], bh = bhn[c];
+#pragma unroll
+        for (int i = 0; i < WR3; ++i) {
+          const int p = i >> 1;
+          const float sr = (i & 1) ? ar[p][j].y : ar[p][j].x, sz = (i & 1) ? az[p][j].y : az[p][j].x;
+          const float sn = (i & 1) ? an[p][j].y : an[p][j].x, sh = (i & 1) ? ahn[p][j].y : ahn[p][j].x;
+          const float rgate = sigmoidf_(sr + bir);
+          const float zgate = sigmoidf_(sz + biz);
+          const float cand = tanhf(sn + bin + rgate * (sh + bh));
+          hn[i][j] = (1.f - zgate) * cand + zgate * b1[c * R3S + r0 + i];   // previous carry (parked in b1)
+        }
+      }
+    }
+    __syncwarp();                                                   // every lane is done reading b0 / b1
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = lane + 32 * j;
+#pragma unroll
+      for (int i4 = 0; i4 < WR3 / 4; ++i4)
+        *reinterpret_cast<float4*>(b0 + c * R3S + r0 + 4 * i4) =
+            make_float4(hn[4 * i4][j], hn[4 * i4 + 1][j], hn[4 * i4 + 2][j], hn[4 * i4 + 3][j]);
+#pragma unroll
+      for (int i = 0; i < WR3; ++i)                                 // new carry, coalesced across lanes
+        if (i < rows) g.rnn_out[row_off(row0 + i) + c] = hn[i][j];
+    }
+    __syncwarp();
+    const float* feat = b0;
+    if (policy) {
+      warp_dense64<WR3, R3S>(b0, scale_w, scale_b, b1, r0, lane);   // ScaleHid (policy.py:67)
+      __syncwarp();
+      feat = b1;
+    }
+    {   // out: [64] -> 4 columns; lane = (row, column)
+      const int rr = lane >> 2, col = lane & 3;
+      float acc = out_b[col];
+#pragma unroll 8
+      for (int k = 0; k < HID; ++k) acc = fmaf(feat[k * R3S + r0 + rr], out_w[k * 4 + col], acc);
+      o4[col * R3S + r0 + rr] = acc;
+    }
+    __syncwarp();
+    if (lane < rows) {
+      const int r = r0 + lane;
+      const long row = row0 + lane;
+      const long gi = row / nr; const int i = (int)(row - gi * nr);
+      const long env = gi / g.n_slots; const int slot = (int)(gi - env * g.n_slots);
+      if (policy) {
+        policy_tail(g, o4[r], o4[R3S + r], o4[2 * R3S + r], o4[3 * R3S + r], (int)env, slot, i, n);
+      } else {
+        float* vo = g.value + ((((size_t)env * g.out_pitch + slot) * nr + i) * net.n_out);
+        for (int c = 0; c < net.n_out; ++c) vo[c] = o4[c * R3S + r];
+      }
+    }
+  }
+}
+
+
 int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const float* params,
                   const GnnArgs& g_in, int sms) {
   if (!g_in.rnn_out || g_in.rnn_out == g_in.rnn_in) return DGPPO_V2_UNSUPPORTED;
@@ -713,7 +881,18 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   const long total_rows = (long)g.n_graphs * nr;
   const long h_tiles = (total_rows + R - 1) / R;             // CTAs worth of 8-row warp tiles
   const int grid2 = h_tiles < sms ? (int)h_tiles : sms;
-  const char* wr8 = getenv("DGPPO_HEAD_WR8");
+  const char* hv = getenv("DGPPO_HEAD");                    // "wide" (default) | "wr4" | "wr8"
+  const size_t wide_smem = ((size_t)pl.hw_fl + 2 * HID * R3S + 4 * R3S) * sizeof(float);
+  const bool want_wide = !hv || hv[0] == 'w' && hv[1] == 'i';
+  if (want_wide && wide_smem <= 227 * 1024) {
+    const long w_tiles = (total_rows + R3 - 1) / R3;
+    const int grid3 = w_tiles < sms ? (int)w_tiles : sms;
+    err = cudaFuncSetAttribute(head_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem);
+    if (err != cudaSuccess) return (int)err;
+    head_kernel_wide<<<grid3, 512, wide_smem, st>>>(P, g, pl, params);
+    return (int)cudaGetLastError();
+  }
+  const char* wr8 = (hv && hv[2] == '8') ? "1" : "0";
   if (wr8 && wr8[0] == '1') {
     err = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.head_smem_bytes);
     if (err != cudaSuccess) return (int)err;
