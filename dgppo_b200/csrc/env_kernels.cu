@@ -287,6 +287,7 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
 // coalesced.
 constexpr int K3_THREADS = 128;
 
+template <int SD>          // state_dim is a template parameter: the index arithmetic divides by it
 __global__ void __launch_bounds__(K3_THREADS)
 build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
                    const float* __restrict__ goal, const float* __restrict__ obs_nodes,
@@ -296,8 +297,9 @@ build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
   extern __shared__ float smem[];
   const int env = blockIdx.x;
   if (env >= b) return;
-  const int n = d.n, g = d.g, sd = d.sd, nd = d.nd, N = d.N, E = d.E;
-  const bool lid = is_lidar(k.kind), bic = is_bicycle(k.kind);
+  constexpr int sd = SD, nd = SD + 3;
+  const int n = d.n, g = d.g, N = d.N, E = d.E;
+  const bool lid = is_lidar(k.kind), bic = (SD == 5);
   const int ow = lid ? 2 : 4;                    // floats per obstacle node
   float* sa = smem;                              // agent states   n*sd
   float* sg = sa + n * sd;                       // goal states    g*sd
@@ -459,8 +461,11 @@ extern "C" int dgppo_build_graph(void* stream, const DgppoEnvCfg* cfg, const flo
   const int ow = is_lidar(cfg->kind) ? 2 : 4;
   const size_t smem = (size_t)(d.n * d.sd + d.g * d.sd + (d.n + d.g) * 4 + d.n_on * ow) * sizeof(float);
   if (smem > 48 * 1024) return DGPPO_ENOTSUP;
-  build_graph_kernel<<<b, K3_THREADS, smem, (cudaStream_t)stream>>>(
-      k, d, agent, goal, obs_nodes, nodes, edges, states, receivers, senders, node_type,
-      n_node, n_edge, pitch, b);
+  if (d.sd == 5)
+    build_graph_kernel<5><<<b, K3_THREADS, smem, (cudaStream_t)stream>>>(
+        k, d, agent, goal, obs_nodes, nodes, edges, states, receivers, senders, node_type, n_node, n_edge, pitch, b);
+  else
+    build_graph_kernel<4><<<b, K3_THREADS, smem, (cudaStream_t)stream>>>(
+        k, d, agent, goal, obs_nodes, nodes, edges, states, receivers, senders, node_type, n_node, n_edge, pitch, b);
   return (int)cudaGetLastError();
 }
