@@ -287,9 +287,40 @@ def run_gpu(args):
     # the same through the full public call: algo.collect(params, keys) = device-side reset (K0 rejection
     # sampler) + LiDAR + graph + rollout.  Reported beside the metric; the metric itself uses synthetic states.
     keys = np.arange(b, dtype=np.uint64) + 7919 * (rank + 1)
-    algo.collect(algo.params, keys, record=record)
-    ms_api = timed(lambda: algo.collect(algo.params, keys, record=record), max(1, args.steps // 2))
-    ms_api /= max(1, args.steps // 2)
+    try:
+        algo.collect(algo.params, keys, record=record)
+        ms_api = timed(lambda: algo.collect(algo.params, keys, record=record), max(1, args.steps // 2))
+        ms_api /= max(1, args.steps // 2)
+    except RuntimeError as exc:       # e.g. C5 at the default area: the reference's sampler cannot place 64 + 64
+        ms_api, api_err = None, str(exc)
+
+    # update pre-pass (dgppo.py:204-273) on the record just collected: Vl scan,
+    # Vh over all (b, T+1) graphs, Dec-OCP GAE, CBF advantage merge.  Reported beside the metric.
+    prepass = None
+    if not args.no_prepass:
+        if ms_api is not None:
+            ro = algo.collect(algo.params, keys, record=record)
+        else:
+            ro = step_resident(False)
+
+        def ev_time(fn):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return out, e0.elapsed_time(e1)
+
+        (Vl, _), ms_vl = ev_time(lambda: algo.scan_Vl(ro))
+        Vh, ms_vh = ev_time(lambda: algo._value_record("Vh", ro, None))
+        (Qh, Ql), ms_gae = ev_time(lambda: algo.gae(ro.costs, -ro.rewards, Vh, Vl))
+        _, ms_cbf = ev_time(lambda: algo.cbf_advantage(Ql, Vl, Vh, 0))
+        prepass = {"ms": {"scan_Vl": ms_vl, "Vh": ms_vh, "gae": ms_gae, "cbf_advantage": ms_cbf},
+                   "graphs": b * (T + 1), "note": "one pass over the stochastic record; update() runs Vh + GAE "
+                   "twice (stochastic + deterministic record) and one more deterministic rollout"}
+        del Vl, Vh, Qh, Ql, ro
 
     units = b * T * n * world
     value = units * args.steps / (ms * 1e-3)
@@ -322,10 +353,13 @@ def run_gpu(args):
                                  "see DESIGN.md for the compute roofline"},
             "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof),
             "rollout_streams": algo.rollout_chunks,
-            "api_collect_with_reset": {"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT},
+            "api_collect_with_reset": ({"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT}
+                                       if ms_api is not None else {"unavailable": api_err}),
             "rollout_hbm": {"unique_record_bytes_per_env_step": rec_bytes, "achieved_gbs": rollout_gbs,
                             "frac_of_hbm": rollout_gbs / hbm},
         }
+        if prepass is not None:
+            line["update_prepass"] = prepass
         if not args.no_cpu and world == 1:
             rate, sample = cpu_rollout_rate(w, target_s=12.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -343,6 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", type=str, default="C3", choices=list(WORKLOADS))
+    ap.add_argument("--no-prepass", action="store_true", help="skip the update pre-pass timing (Vl / Vh / GAE / CBF)")
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--scaling", type=str, default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

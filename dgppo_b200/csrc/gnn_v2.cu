@@ -444,6 +444,315 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
   }
 }
 
+// ------------------------------------------------- GNN layers, large graphs
+// n > R2 (e.g. LidarSpread n = 64): ONE graph per tile, its node features
+// resident in smem, receiver rows processed in chunks of R2.  Attention works on
+// the COMPACTED list of live slots (a row of C5 has 136 slots, about half of
+// them masked): lanes first compact (slot, sender) pairs, then score the live
+// entries 32 at a time, keep exp(score - max) unnormalised in the list and fold
+// 1/sum into the column sums at the end.  Scratch per warp: degp float4.
+
+// 16 per-lane values -> warp sums, 16 shuffles (transpose-reduce).  On return
+// v[0] of lane L is the warp sum of value k(L) = the bits (L>>1) of L reversed:
+//   k = 8*(L>>4 & 1) + 4*(L>>3 & 1) + 2*(L>>2 & 1) + (L>>1 & 1).
+__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int INX>
+__device__ __forceinline__ void attention_row_big(int r, bool live, int lane, const unsigned short* srow, int deg, int degp,
+                                                  const float* qrow, int IN, float isd,
+                                                  const float* X, int XS, const float4* ed, int i_agent,
+                                                  int n, int n_ag, int n_ao, float4* al, float* z) {
+  const int INA = IN + 5;
+  float* zc = z + r;
+  if (!live) {
+    for (int c = lane; c < H * INA; c += 32) zc[c * RS2] = 0.f;
+    return;
+  }
+  // ---- compact the live slots: al[pos].w = (slot << 16) | (sender * XS)
+  int count = 0;
+  for (int t0 = 0; t0 < degp; t0 += 32) {
+    const int t = t0 + lane;
+    const int s = (t < deg) ? (int)srow[t] : 0xffff;             // 0xffff: masked slot
+    const unsigned m = __ballot_sync(0xffffffffu, s != 0xffff);
+    if (s != 0xffff) al[count + __popc(m & ((1u << lane) - 1u))].w = __int_as_float((t << 16) | (s * XS));
+    count += __popc(m);
+  }
+  __syncwarp();
+  // ---- scores of the live entries, running max per head
+  float mx[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) mx[h] = -INFINITY;
+  for (int p0 = 0; p0 < count; p0 += 32) {
+    const int p = p0 + lane;
+    if (p < count) {
+      const int pk = __float_as_int(al[p].w);
+      const float* xp = X + (pk & 0xffff);
+      float acc[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) acc[h] = qrow[h * QTS + IN];
+#pragma unroll
+      for (int c = 0; c < INX; c += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + c);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float4 qv = *reinterpret_cast<const float4*>(qrow + h * QTS + c);
+          acc[h] = fmaf(qv.x, xv.x, acc[h]); acc[h] = fmaf(qv.y, xv.y, acc[h]);
+          acc[h] = fmaf(qv.z, xv.z, acc[h]); acc[h] = fmaf(qv.w, xv.w, acc[h]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) { acc[h] *= isd; mx[h] = fmaxf(mx[h], acc[h]); }
+      al[p].x = acc[0]; al[p].y = acc[1]; al[p].z = acc[2];
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) mx[h] = warp_max(mx[h]);
+  // ---- exp, row sums, weighted edge features (unnormalised)
+  float l[H] = {0.f, 0.f, 0.f};
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = 0.f;
+  auto edge_of = [&](int p) -> float4 {             // edge features of list entry p (global, L2)
+    if (p >= count) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const int t = __float_as_int(al[p].w) >> 16;
+    const int e = (t < n) ? i_agent * n + t
+                          : ((t < n + n_ag) ? n * n + i_agent * n_ag + (t - n)
+                                            : n * n + n * n_ag + i_agent * n_ao + (t - n - n_ag));
+    return __ldg(ed + e);
+  };
+  float4 ef_next = edge_of(lane);
+  for (int p0 = 0; p0 < count; p0 += 32) {
+    const int p = p0 + lane;
+    const float4 ef = ef_next;
+    ef_next = edge_of(p + 32);                        // in flight while this chunk is processed
+    if (p < count) {
+      float4 a = al[p];
+      a.x = expf(a.x - mx[0]); a.y = expf(a.y - mx[1]); a.z = expf(a.z - mx[2]);
+      al[p] = a;
+      l[0] += a.x; l[1] += a.y; l[2] += a.z;
+      v[0] = fmaf(a.x, ef.x, v[0]); v[1] = fmaf(a.x, ef.y, v[1]); v[2] = fmaf(a.x, ef.z, v[2]); v[3] = fmaf(a.x, ef.w, v[3]);
+      v[4] = fmaf(a.y, ef.x, v[4]); v[5] = fmaf(a.y, ef.y, v[5]); v[6] = fmaf(a.y, ef.z, v[6]); v[7] = fmaf(a.y, ef.w, v[7]);
+      v[8] = fmaf(a.z, ef.x, v[8]); v[9] = fmaf(a.z, ef.y, v[9]); v[10] = fmaf(a.z, ef.z, v[10]); v[11] = fmaf(a.z, ef.w, v[11]);
+    }
+  }
+  float inv_l[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) { l[h] = warp_sum(l[h]); inv_l[h] = (l[h] > 0.f) ? 1.f / l[h] : 0.f; }
+  warp_reduce16(v, lane);
+  __syncwarp();
+  {
+    const int k = 8 * ((lane >> 4) & 1) + 4 * ((lane >> 3) & 1) + 2 * ((lane >> 2) & 1) + ((lane >> 1) & 1);
+    if (!(lane & 1) && k < H * 4) {
+      const int eh = k >> 2, ej = k & 3;
+      const float il = (eh == 0) ? inv_l[0] : ((eh == 1) ? inv_l[1] : inv_l[2]);
+      zc[(eh * INA + IN + 1 + ej) * RS2] = v[0] * il;
+      if (ej == 0) zc[(eh * INA + IN) * RS2] = (count > 0) ? 1.f : 0.f;
+    }
+  }
+  // ---- weighted sender features: lanes = feature columns (x NG slot groups)
+  {
+    constexpr int NG = 32 / INX;
+    const int c = lane % INX, tq = lane / INX;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int t = tq; t < count; t += NG) {
+      const float4 av = al[t];
+      const float x = X[(__float_as_int(av.w) & 0xffff) + c];
+      a0 = fmaf(av.x, x, a0); a1 = fmaf(av.y, x, a1); a2 = fmaf(av.z, x, a2);
+    }
+    if (NG > 1) {
+#pragma unroll
+      for (int o = INX; o < 32; o <<= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+    }
+    if (tq == 0 && c < IN) {
+      zc[c * RS2] = a0 * inv_l[0]; zc[(INA + c) * RS2] = a1 * inv_l[1]; zc[(2 * INA + c) * RS2] = a2 * inv_l[2];
+    }
+  }
+  __syncwarp();
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256, 1)
+gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params) {
+  extern __shared__ __align__(16) float smem[];
+  const int nth = blockDim.x, nwarps = nth >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ws = smem;                                    // GNN weights
+  float* x0 = ws + pl.w_fl;                            // [M][8]
+  float* x1 = x0 + pl.x0_fl;                           // [M][36]
+  float* xr = x1 + pl.x1_fl;                           // [32][RS2]
+  float* qt = xr + 32 * RS2;                           // [R2][H][QTS]; split-K partial after the attention
+  float* z = qt + R2 * H * QTS;                        // [112][RS2]; Vl: last-layer rows after the GEMM
+  unsigned short* sidx = reinterpret_cast<unsigned short*>(z + 112 * RS2);   // [n][degp] sender of every slot (0xffff: masked)
+  float* scr = reinterpret_cast<float*>(sidx) + pl.sidx_fl;   // per-warp compacted lists; split-K partial
+  int* tab = reinterpret_cast<int*>(scr + pl.scr_fl);  // [64] gslot, [96] rslot
+  float* vlsum = reinterpret_cast<float*>(tab + 128);  // [64] Vl: running sum over the agents
+  unsigned char* nflag = reinterpret_cast<unsigned char*>(vlsum + HID);   // [M] node is an active sender
+
+  for (int i = threadIdx.x; i < pl.w_fl / 4; i += nth) cp_async16(ws + 4 * i, params + pl.w_off + 4 * i);
+  cp_async_wait_all();
+  __syncthreads();
+  auto wptr = [&](const float* p) { return ws + ((p - params) - pl.w_off); };
+
+  const int n = g.n, N = g.N, nd = g.nd, deg = pl.deg, degp = pl.degp;
+  const int M = N - 1, pad = N - 1;
+  const int n_chunks = (n + R2 - 1) / R2;
+  const bool vl = net.kind == DGPPO_NET_VL;
+  float4* my_al = reinterpret_cast<float4*>(scr) + (size_t)warp * degp;
+
+  for (int gi = blockIdx.x; gi < g.n_graphs; gi += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+      tab[64] = env * g.pitch + slot;
+      tab[96] = env * g.rnn_pitch + slot;
+    }
+    for (int i = threadIdx.x; i < (M + 3) / 4; i += nth) reinterpret_cast<int*>(nflag)[i] = 0;
+    if (threadIdx.x < HID) vlsum[threadIdx.x] = 0.f;
+    __syncthreads();
+    const size_t gslot = (size_t)tab[64];
+    {
+      const float* src = g.nodes + gslot * N * nd;
+      if (nd == X0S) {
+        for (int j = threadIdx.x; j < M * X0S; j += nth) cp_async4(x0 + j, src + j);
+      } else {
+        for (int j = threadIdx.x; j < M * 7; j += nth) {
+          const int node = j / 7, c = j - node * 7;
+          cp_async4(x0 + node * X0S + c, src + j);
+        }
+        for (int j = threadIdx.x; j < M; j += nth) x0[j * X0S + 7] = 0.f;
+      }
+    }
+    const float4* ed = reinterpret_cast<const float4*>(g.edges + gslot * g.E * 4);
+    const int* recv = g.recv + gslot * g.E;
+    const int* send = g.send + gslot * g.E;
+    // ---- sender table of every receiver row, once per graph (loads are independent: no branch between them)
+    for (int idx = threadIdx.x; idx < n * degp; idx += nth) {
+      const int i = idx / degp, t = idx - i * degp;
+      int s = 0xffff;
+      if (t < deg) {
+        const int e = (t < n) ? i * n + t
+                              : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
+                                                  : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
+        const int rv = __ldg(recv + e), sd = __ldg(send + e);
+        if (rv != pad) { s = sd; if (NL > 1) nflag[sd] = 1; }
+      }
+      sidx[idx] = (unsigned short)s;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const float* X = x0; int XS = X0S;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const LayerP& P = net.L[l];
+      const int IN = P.in, D = P.d, INP = round4(IN + 1), INA = IN + 5;
+      const bool last = (l == NL - 1);
+      const float *wqk = wptr(P.wqk), *wagg = wptr(P.wagg), *wu = wptr(P.wu), *bu = wptr(P.bu);
+      const float isd = 1.f / sqrtf((float)D);
+
+      for (int rc = 0; rc < n_chunks; ++rc) {
+        const int a0 = rc * R2, rows = min(R2, n - a0);
+        // ---- transposed receiver features of the chunk's rows
+        for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // xr[c][r] = X[a0 + r][c]
+          const int c = idx / R2, r = idx % R2;
+          xr[c * RS2 + r] = (r < rows && c < IN) ? X[(size_t)(a0 + r) * XS + c] : 0.f;
+        }
+        __syncthreads();
+        gemm_ws<R2, RS2, 2>(xr, 0, IN, wqk, H * INP, 1.f, nullptr, 0, nullptr, 0, H * INP / 4, 0, nwarps,
+                            [&](int r0, int c0, float (&acc)[2][4]) {
+                              const int h = c0 / INP, c = c0 - h * INP;
+                              const float4 bb = *reinterpret_cast<const float4*>(wqk + IN * H * INP + c0);
+#pragma unroll
+                              for (int i = 0; i < 2; ++i)
+                                *reinterpret_cast<float4*>(qt + ((r0 + i) * H + h) * QTS + c) =
+                                    make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+                            });
+        __syncthreads();
+        for (int r = warp; r < R2; r += nwarps) {
+          if (l == 0) attention_row_big<X0S>(r, r < rows, lane, sidx + (a0 + r) * degp, deg, degp, qt + r * H * QTS, IN, isd,
+                                             X, XS, ed, a0 + r, n, g.n_ag, g.n_ao, my_al, z);
+          else        attention_row_big<32>(r, r < rows, lane, sidx + (a0 + r) * degp, deg, degp, qt + r * H * QTS, IN, isd,
+                                            X, XS, ed, a0 + r, n, g.n_ag, g.n_ao, my_al, z);
+        }
+        __syncthreads();
+        const int KZ = H * INA, kh = KZ / 2, hw = nwarps / 2;
+        float* part_hi = qt;                                            // [R2][64]
+        float* part_lo = scr;                                           // [R2][64]
+        auto store_part = [&](float* dstp) {
+          return [=](int r0, int c0, float (&acc)[2][4]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              *reinterpret_cast<float4*>(dstp + (r0 + i) * 64 + c0) =
+                  make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          };
+        };
+        gemm_ws<R2, RS2, 2>(z, kh, KZ, wagg, D, 1.f / H, nullptr, 0, nullptr, 0, D / 4, hw, nwarps - hw,
+                            store_part(part_hi));
+        gemm_ws<R2, RS2, 2>(z, 0, kh, wagg, D, 1.f / H, xr, IN, wu, D, D / 4, 0, hw, store_part(part_lo));
+        __syncthreads();
+        float* ob = z;                                                  // Vl only: [64][RS2]
+        for (int idx = threadIdx.x; idx < R2 * (D / 4); idx += nth) {   // combine + bias + relu
+          const int r = idx / (D / 4), c0 = (idx - r * (D / 4)) * 4;
+          const float4 lo = *reinterpret_cast<const float4*>(part_lo + r * 64 + c0);
+          const float4 hi = *reinterpret_cast<const float4*>(part_hi + r * 64 + c0);
+          const float4 v = make_float4(fmaxf(lo.x + hi.x + bu[c0], 0.f), fmaxf(lo.y + hi.y + bu[c0 + 1], 0.f),
+                                       fmaxf(lo.z + hi.z + bu[c0 + 2], 0.f), fmaxf(lo.w + hi.w + bu[c0 + 3], 0.f));
+          if (last && vl) {
+            ob[(c0 + 0) * RS2 + r] = v.x; ob[(c0 + 1) * RS2 + r] = v.y;
+            ob[(c0 + 2) * RS2 + r] = v.z; ob[(c0 + 3) * RS2 + r] = v.w;
+          } else if (r < rows) {
+            if (!last) *reinterpret_cast<float4*>(x1 + (size_t)(a0 + r) * X1S + c0) = v;
+            else       *reinterpret_cast<float4*>(g.rnn_out + ((size_t)tab[96] * n + a0 + r) * HID + c0) = v;
+          }
+        }
+        if (last && vl) {
+          __syncthreads();
+          if (threadIdx.x < HID) {                        // sequential over agents, as the small-graph kernel
+            float sacc = vlsum[threadIdx.x];
+            for (int r = 0; r < rows; ++r) sacc += ob[threadIdx.x * RS2 + r];
+            vlsum[threadIdx.x] = sacc;
+          }
+        }
+        __syncthreads();
+      }
+      if (!last) {                          // non-agent nodes that send in the next layer
+        for (int idx = threadIdx.x; idx < (M - n) * 8; idx += nth) {
+          const int s = n + (idx >> 3), c0 = (idx & 7) * 4;
+          if (!nflag[s]) continue;
+          const float* x = X + (size_t)s * XS;
+          float b0 = bu[c0], b1 = bu[c0 + 1], b2 = bu[c0 + 2], b3 = bu[c0 + 3];
+          for (int c = 0; c < IN; ++c) {
+            const float xv = x[c];
+            const float4 w = *reinterpret_cast<const float4*>(wu + c * D + c0);
+            b0 = fmaf(xv, w.x, b0); b1 = fmaf(xv, w.y, b1); b2 = fmaf(xv, w.z, b2); b3 = fmaf(xv, w.w, b3);
+          }
+          *reinterpret_cast<float4*>(x1 + (size_t)s * X1S + c0) =
+              make_float4(fmaxf(b0, 0.f), fmaxf(b1, 0.f), fmaxf(b2, 0.f), fmaxf(b3, 0.f));
+        }
+        __syncthreads();
+        X = x1; XS = X1S;
+      }
+    }
+    if (vl && threadIdx.x < HID)           // centralised Vl: mean over the agents (value.py:28-31)
+      g.rnn_out[(size_t)tab[96] * HID + threadIdx.x] = vlsum[threadIdx.x] / (float)n;
+  }
+}
+
 // ------------------------------------------------------------------ head
 // Each WARP owns 8 rows of the tile end to end (head MLP -> LayerNorm -> GRU ->
 // tails); lanes span the output columns {lane, lane + 32}.  The A operand (the
@@ -836,9 +1145,9 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
 int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const float* params,
                   const GnnArgs& g_in, int sms) {
   if (!g_in.rnn_out || g_in.rnn_out == g_in.rnn_in) return DGPPO_V2_UNSUPPORTED;
-  if (g_in.n > R2) return DGPPO_V2_UNSUPPORTED;
   GnnArgs g = g_in;
-  g.G = R2 / g.n;
+  const bool big = g.n > R2;
+  g.G = big ? 1 : R2 / g.n;
   GnnV2Plan pl;
   pl.w_off = L.wqk[0];
   pl.w_fl = L.d0w - L.wqk[0];
@@ -850,13 +1159,15 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   if (P.kind == DGPPO_NET_VL && pl.x0_fl < HID * RS2) pl.x0_fl = HID * RS2;
   pl.x1_fl = (P.n_layers == 2) ? pl.m_cap * X1S : 0;
   pl.degp = ((pl.deg + 31) / 32) * 32;
-  if (pl.degp > 64) return DGPPO_V2_UNSUPPORTED;
-  pl.sidx_fl = R2 * pl.degp;
+  if (!big && pl.degp > 64) return DGPPO_V2_UNSUPPORTED;
+  if (big && ((long)pl.m_cap * X1S > 0xffff || pl.degp > 0x7fff)) return DGPPO_V2_UNSUPPORTED;   // packed list entries
+  pl.sidx_fl = big ? round4((g.n * pl.degp + 1) / 2) : R2 * pl.degp;    // large graphs: uint16, all rows
   const size_t base_fl = (size_t)pl.w_fl + pl.x0_fl + pl.x1_fl + 32 * RS2 + R2 * H * QTS + 112 * RS2 + pl.sidx_fl +
-                         128 /* tab */ + round4((pl.m_cap + 3) / 4) /* nflag */;
+                         128 /* tab */ + (big ? HID : 0) /* vlsum */ + round4((pl.m_cap + 3) / 4) /* nflag */;
   pl.threads = 256;
-  pl.scr_fl = (pl.threads / 32) * pl.degp * 8;       // also hosts a [R2][64] split-K partial (2048 floats)
-  if (pl.scr_fl < R2 * 64) pl.scr_fl = R2 * 64;      // split-K partial [R2][64]
+  // per-warp attention scratch: small graphs (a, offset) + edge-feature lists, large graphs one float4 list
+  pl.scr_fl = (pl.threads / 32) * pl.degp * (big ? 4 : 8);
+  if (pl.scr_fl < R2 * 64) pl.scr_fl = R2 * 64;      // also hosts the split-K partial [R2][64]
   pl.smem_bytes = (base_fl + pl.scr_fl) * sizeof(float);
   pl.head_smem_bytes = ((size_t)pl.hw_fl + 3 * HID * RS + 4 * RS) * sizeof(float);
   if (pl.smem_bytes > 227 * 1024 || pl.head_smem_bytes > 227 * 1024) return DGPPO_V2_UNSUPPORTED;
@@ -866,7 +1177,18 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
   const int grid1 = n_tiles < 2 * sms ? n_tiles : 2 * sms;
   cudaError_t err;
-  if (P.n_layers == 2) {
+  if (big) {
+    const int gridb = g.n_graphs < sms ? g.n_graphs : sms;
+    if (P.n_layers == 2) {
+      err = cudaFuncSetAttribute(gnn_layers_big_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+      if (err != cudaSuccess) return (int)err;
+      gnn_layers_big_kernel<2><<<gridb, pl.threads, pl.smem_bytes, st>>>(P, g, pl, params);
+    } else {
+      err = cudaFuncSetAttribute(gnn_layers_big_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+      if (err != cudaSuccess) return (int)err;
+      gnn_layers_big_kernel<1><<<gridb, pl.threads, pl.smem_bytes, st>>>(P, g, pl, params);
+    }
+  } else if (P.n_layers == 2) {
     err = cudaFuncSetAttribute(gnn_layers_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (err != cudaSuccess) return (int)err;
     gnn_layers_kernel<2><<<grid1, pl.threads, pl.smem_bytes, st>>>(P, g, pl, params);

@@ -62,6 +62,10 @@ __device__ __forceinline__ bool collides(float cx, float cy, const float* pts, i
 
 constexpr int RESET_WARPS = 4;
 constexpr int RESET_MAX_ITER = 1024;           // env/utils.py:150
+// The reference restarts the whole placement for ever when an area is too crowded to hold the agents
+// (env/utils.py:229-232: a hang).  A kernel must terminate: after this many restarts the last placement
+// is kept and the environment is flagged through n_draws[env] < 0, which the host turns into an error.
+constexpr int RESET_MAX_RESTARTS = 16;
 
 __global__ void __launch_bounds__(RESET_WARPS * 32)
 reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* __restrict__ agent,
@@ -105,7 +109,7 @@ reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* 
   // ---- get_node_goal_rng (env/utils.py:139-244)
   for (int j = lane; j < 2 * n; j += 32) { st[j] = 0.f; gl[j] = 0.f; }
   __syncwarp();
-  int agent_id = 0;
+  int agent_id = 0, restarts = 0;
   while (agent_id < n) {
     // agent candidate: redraw while it collides / lies in an obstacle, at most max_iter times
     float2 u = rng.next2();
@@ -131,6 +135,7 @@ reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* 
     __syncwarp();
     ++agent_id;
     if (it_a >= RESET_MAX_ITER || it_g >= RESET_MAX_ITER) {      // no solution found: start over (utils.py:229-232)
+      if (++restarts > RESET_MAX_RESTARTS) continue;            // infeasible: keep going with what we have
       agent_id = 0;
       for (int j = lane; j < 2 * n; j += 32) { st[j] = 0.f; gl[j] = 0.f; }
       __syncwarp();
@@ -152,6 +157,7 @@ reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* 
         ++guard; u = rng.next2();
         ox = fadd(lo, fmul(u.x, fsub(hi, lo))); oy = fadd(lo, fmul(u.y, fsub(hi, lo)));
       }
+      if (guard >= (1 << 20)) restarts = RESET_MAX_RESTARTS + 1;   // flag: no room for the obstacle
       if (lane == 0) { oo[4 * o] = ox; oo[4 * o + 1] = oy; oo[4 * o + 2] = 0.f; oo[4 * o + 3] = 0.f; }
     }
   } else {
@@ -171,7 +177,7 @@ reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* 
       if (sd == 5) { ao[i * sd + 2] = cs; ao[i * sd + 3] = sn; }
     }
   }
-  if (n_draws && lane == 0) n_draws[env] = (int)rng.ctr;
+  if (n_draws && lane == 0) n_draws[env] = (restarts > RESET_MAX_RESTARTS) ? -1 : (int)rng.ctr;
 }
 
 }  // namespace dgppo

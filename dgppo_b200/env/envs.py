@@ -94,10 +94,15 @@ def _reset_kernel(env, seeds: np.ndarray, dev, obs_len=(0.0, 0.0), theta=(0.0, 0
     goal = torch.empty((b, n, sd), dtype=torch.float32, device=dev)
     obst = torch.empty((b, n_obs, _lib.OBS_STRIDE if lidar else 4), dtype=torch.float32, device=dev) \
         if n_obs > 0 else None
+    draws = torch.empty((b,), dtype=torch.int32, device=dev)
     cfg = env.env_cfg()
     _lib.check(_lib.lib().dgppo_reset(stream_ptr(), C.byref(cfg), ptr(keys), float(obs_len[0]), float(obs_len[1]),
-                                       float(theta[0]), float(theta[1]), ptr(agent), ptr(goal), ptr(obst), None, b),
-               "dgppo_reset")
+                                       float(theta[0]), float(theta[1]), ptr(agent), ptr(goal), ptr(obst),
+                                       ptr(draws), b), "dgppo_reset")
+    if bool((draws < 0).any()):
+        raise RuntimeError(f"reset: area_size={env.area_size} cannot hold {n} agents + goals"
+                           f"{' + ' + str(n_obs) + ' obstacles' if n_obs else ''} at the required spacing "
+                           "(the reference's sampler does not terminate for this configuration)")
     return agent, goal, obst
 
 

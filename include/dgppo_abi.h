@@ -101,7 +101,10 @@ int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out);
  *   obs_len_lo/hi, theta_lo/hi : PARAMS["obs_len_range"], obstacle angle range
  *             ([0, 2 pi) LidarEnv, [-pi, pi) bicycle); ignored for MPE
  *   agent, goal (b, n, state_dim) out; obstacles (b, n_obs, DGPPO_OBS_STRIDE) out
- *             (Lidar) or (b, n_obs, 4) out (MPE); n_draws (b) out, nullable.        */
+ *             (Lidar) or (b, n_obs, 4) out (MPE); n_draws (b) out, nullable:
+ *             random draws consumed, or -1 when the area cannot hold the agents
+ *             (more than 16 restarts of the placement; the reference loops for
+ *             ever in that case, env/utils.py:229-232).                            */
 int dgppo_reset(void* stream, const DgppoEnvCfg* cfg, const uint64_t* keys,
                 double obs_len_lo, double obs_len_hi, double theta_lo, double theta_hi,
                 float* agent, float* goal, float* obstacles, int32_t* n_draws, int32_t b);

@@ -13,6 +13,7 @@ from . import env_np
 F = np.float32
 MASK = (1 << 64) - 1
 MAX_ITER = 1024
+MAX_RESTARTS = 16          # kernel guard (csrc/reset_kernels.cu): the reference itself would loop for ever
 
 
 def splitmix64(x: int) -> int:
@@ -71,7 +72,7 @@ def reset_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3), theta_range=N
     min_dist = F((2.2 if lid else 2.0) * cfg.car_radius)
     half = F(min_dist / F(2))
     st, gl = np.zeros((n, 2), F), np.zeros((n, 2), F)
-    agent_id = 0
+    agent_id = restarts = 0
     while agent_id < n:
         u = rng.next2()
         c = (F(u[0] * A), F(u[1] * A))
@@ -92,6 +93,9 @@ def reset_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3), theta_range=N
         gl[agent_id] = g
         agent_id += 1
         if it_a >= MAX_ITER or it_g >= MAX_ITER:
+            restarts += 1
+            if restarts > MAX_RESTARTS:
+                continue
             agent_id = 0
             st[:] = 0
             gl[:] = 0

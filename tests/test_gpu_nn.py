@@ -39,11 +39,12 @@ def _close(got, ref32, ref64, what):
     assert err.max() <= 20 * max(err32.max(), 1e-7 * scale) + ATOL * scale * 0.1, msg
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5", "target", "noobs_lidar", "one_agent"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5", "target", "noobs_lidar", "one_agent",
+                                  "n24", "mpe20", "target40", "dense20"])
 @pytest.mark.parametrize("stochastic", [True, False])
 def test_policy_forward(name, stochastic):
     cfg = CONFIGS[name]
-    b = 5 if cfg.n >= 64 else 37           # not a multiple of the tile size
+    b = 5 if cfg.n >= 64 else (11 if cfg.n > 16 else 37)           # not a multiple of the tile size
     g = _graph(cfg, b, 21)
     tree = P.init_policy_params(cfg.node_dim, 4, 2, 2, seed=3, jitter=0.1, scale_final=1.0)
     nc = P.net_cfg(_lib.NET_POLICY, cfg.node_dim, 4, 2, 2)
@@ -84,10 +85,10 @@ def test_policy_log_prob_tails():
     assert agree.mean() > 0.9
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5", "n24", "mpe20"])
 def test_vh_forward(name):
     cfg = CONFIGS[name]
-    b = 5 if cfg.n >= 64 else 37
+    b = 5 if cfg.n >= 64 else (11 if cfg.n > 16 else 37)
     g = _graph(cfg, b, 31)
     tree = P.init_value_params(cfg.node_dim, 4, 2, 1, seed=5, jitter=0.1)
     nc = P.net_cfg(_lib.NET_VH, cfg.node_dim, 4, 1, 2)
@@ -99,10 +100,10 @@ def test_vh_forward(name):
     _close(v, v32, v64, f"Vh {name}")
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5", "n24", "mpe20", "target40"])
 def test_vl_forward(name):
     cfg = CONFIGS[name]
-    b = 37
+    b = 5 if cfg.n >= 64 else (11 if cfg.n > 16 else 37)
     g = _graph(cfg, b, 41)
     tree = P.init_value_params(cfg.node_dim, 4, 1, 2, seed=6, jitter=0.1)
     nc = P.net_cfg(_lib.NET_VL, cfg.node_dim, 4, 2, 1)

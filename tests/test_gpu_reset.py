@@ -85,3 +85,16 @@ def test_reset_invariants_at_scale(name):
     a2, _, _, _ = _run(cfg, np.arange(b, dtype=np.uint64) * 977 + 5)
     np.testing.assert_array_equal(agent, a2)
     assert len({tuple(x) for x in agent[:, 0, :2].round(6)}) > b * 0.99
+
+
+def test_reset_infeasible_area_terminates_and_is_flagged():
+    """64 agents + 64 goals + 64 obstacles do not fit the default 1.5 x 1.5 area: the reference's sampler
+    restarts for ever (env/utils.py:229-232); the kernel gives up after 16 restarts, flags the env through
+    n_draws = -1, and the host API raises."""
+    cfg = env_np.EnvCfg(env_np.LIDAR_SPREAD, n=64, n_obs=64)
+    _, _, _, nd = _run(cfg, np.arange(8, dtype=np.uint64))
+    assert (nd == -1).all()
+    from dgppo_b200.env import make_env
+    env = make_env("LidarSpread", num_agents=64, num_obs=64)
+    with pytest.raises(RuntimeError, match="cannot hold"):
+        env.reset(np.arange(4, dtype=np.uint64))
