@@ -346,8 +346,13 @@ def run_gpu(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps * (5 * T + 2 if lidar else 4 * T + 1),   # policy = gnn_layers + head
             "clocks": clocks,
-            "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel", "bound": "hbm",
-                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel_wide", "bound": "hbm",
+                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                         # dram__bytes_read + dram__bytes_write per launch pair from the committed ncu --set full
+                         # capture (C3, 4096 envs): gnn_layers 27.62 MB + head 17.54 MB read, 0.01 MB written
+                         "traffic": 45.18e6 if (args.workload == "C3" and b == 4096) else None,
+                         "traffic_source": "profiles/r1_policy_v4.ncu.txt",
+                         "algorithmic_bytes_per_launch": pol_bytes * b,
                          "peak_source": which,
                          "note": "FP32-FFMA bound kernel reported against HBM as BASELINE's metric asks; "
                                  "see DESIGN.md for the compute roofline"},

@@ -185,19 +185,36 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
       ef[j] = __ldg(ed + e);
     }
   }
+  {                                               // jraph.segment_softmax over the row's slots;
+    float mx[H], l[H];                            // the three heads' shuffle chains run interleaved
 #pragma unroll
-  for (int h = 0; h < H; ++h) {                   // jraph.segment_softmax over the row's slots
-    float mx = sc[0][h];
+    for (int h = 0; h < H; ++h) {
+      mx[h] = sc[0][h];
 #pragma unroll
-    for (int j = 1; j < J; ++j) mx = fmaxf(mx, sc[j][h]);
-    mx = warp_max(mx);
-    float p[J], l = 0.f;
+      for (int j = 1; j < J; ++j) mx[h] = fmaxf(mx[h], sc[j][h]);
+    }
 #pragma unroll
-    for (int j = 0; j < J; ++j) { p[j] = (sv[j] >= 0) ? expf(sc[j][h] - mx) : 0.f; l += p[j]; }
-    l = warp_sum(l);
-    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    for (int o = 16; o; o >>= 1) {
 #pragma unroll
-    for (int j = 0; j < J; ++j) sc[j][h] = p[j] * inv_l;
+      for (int h = 0; h < H; ++h) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      l[h] = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) { sc[j][h] = (sv[j] >= 0) ? expf(sc[j][h] - mx[h]) : 0.f; l[h] += sc[j][h]; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] += __shfl_xor_sync(0xffffffffu, l[h], o);
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float inv_l = (l[h] > 0.f) ? 1.f / l[h] : 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) sc[j][h] *= inv_l;
+    }
   }
   int count = 0;
 #pragma unroll
@@ -518,7 +535,10 @@ __device__ __forceinline__ void attention_row_big(int r, bool live, int lane, co
     }
   }
 #pragma unroll
-  for (int h = 0; h < H; ++h) mx[h] = warp_max(mx[h]);
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));
+  }
   // ---- exp, row sums, weighted edge features (unnormalised)
   float l[H] = {0.f, 0.f, 0.f};
   float v[16];
