@@ -333,12 +333,21 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
         const int e = (t < n) ? i * n + t
                               : ((t < n + g.n_ag) ? n * n + i * g.n_ag + (t - n)
                                                   : n * n + n * g.n_ag + i * g.n_ao + (t - n - g.n_ag));
-        if (__ldg(g.recv + gslot * g.E + e) != pad) {
-          s = gl * nodes_per + __ldg(g.send + gslot * g.E + e);
+        const int rv = __ldg(g.recv + gslot * g.E + e), sd = __ldg(g.send + gslot * g.E + e);   // independent loads
+        if (rv != pad) {
+          s = gl * nodes_per + sd;
           nflag[s] = 1;
         }
       }
       sidx[idx] = s;
+    }
+    for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // layer 0: xr[c][r] = nodes[agent(r)][c]
+      const int c = idx / R2, r = idx % R2;
+      const int gl = tab[r];
+      float v = 0.f;
+      if (gl >= 0 && c < net.L[0].in)
+        v = __ldg(g.nodes + ((size_t)tab[64 + gl] * N + tab[32 + r]) * nd + c);
+      xr[c * RS2 + r] = v;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -351,14 +360,8 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       const bool last = (l == NL - 1);
       const float *wqk = wptr(P.wqk), *wagg = wptr(P.wagg), *wu = wptr(P.wu), *bu = wptr(P.bu);
 
-      for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // xr[c][r] = X[node(r)][c]
-        const int c = idx / R2, r = idx % R2;
-        const int gl = tab[r];
-        float v = 0.f;
-        if (gl >= 0 && c < IN) v = X[((size_t)gl * nodes_per + tab[32 + r]) * XS + c];
-        xr[c * RS2 + r] = v;
-      }
-      __syncthreads();
+      // xr[c][r] = X[node(r)][c]: filled from global during staging (layer 0) / by the previous
+      // layer's combine step (layer 1)
       // qt[r][h][c] = x_r (Wq_h Wk_h^T)[:, c] + bias row  (query and key merged at pack time)
       gemm_ws<R2, RS2, 2>(xr, 0, IN, wqk, H * INP, 1.f, nullptr, 0, nullptr, 0, H * INP / 4, 0, nwarps,
                           [&](int r0, int c0, float (&acc)[2][4]) {
@@ -443,6 +446,11 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
           const int ia = tab[32 + r];
           if (!last) *reinterpret_cast<float4*>(x1 + ((size_t)gl * nodes_per + ia) * X1S + c0) = v;
           else       *reinterpret_cast<float4*>(g.rnn_out + ((size_t)tab[96 + gl] * n + ia) * HID + c0) = v;   // scratch rows
+        }
+        if (!last) {                                                  // receiver features of the next layer (D == 32)
+          const float4 w = (gl >= 0) ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+          xr[(c0 + 0) * RS2 + r] = w.x; xr[(c0 + 1) * RS2 + r] = w.y;
+          xr[(c0 + 2) * RS2 + r] = w.z; xr[(c0 + 3) * RS2 + r] = w.w;
         }
       }
       if (!last) { X = x1; XS = X1S; }
