@@ -139,3 +139,71 @@ def test_rollout_per_step_parity(name, stochastic):
                 np.testing.assert_allclose(R[k][:, t + 1], g_n[k], rtol=1e-5, atol=1e-6, err_msg=f"{k} t={t + 1}")
             else:
                 assert_bits_equal(R[k][:, t + 1], g_n[k], f"{k} t={t + 1}")
+
+
+@pytest.mark.parametrize("name,b,T", [("C3", 19, 5), ("C2", 7, 4), ("C4", 5, 3), ("C5", 3, 2), ("n24", 5, 3)])
+def test_rollout_writes_stay_inside_the_record(name, b, T):
+    """Every output buffer of dgppo_rollout is allocated with one guard environment in front and one
+    behind, filled with sentinels; the kernels (slot / pitch addressing, tile tails, row chunks of the
+    large-graph GNN kernel) must leave the guards untouched and overwrite every element in between."""
+    cfg = CONFIGS[name]
+    agent, goal, obstacles, mpe_obs = env_np.synthetic_states(cfg, b, 23)
+    rays = env_np.ray_table(cfg.n_rays, cfg.comm_radius) if cfg.is_lidar else None
+    g0 = env_np.reset_graph(cfg, agent, goal, obstacles, mpe_obs, rays)
+    tree = P.init_policy_params(cfg.node_dim, 4, 2, 2, seed=3, jitter=0.1, scale_final=1.0)
+    nc = P.net_cfg(_lib.NET_POLICY, cfg.node_dim, 4, 2, 2)
+    packed = dev(P.pack_params(tree, nc))
+    eps = np.random.default_rng(8).standard_normal((b, T, cfg.n, 2)).astype(F)
+    N, E, n, sd, nd = cfg.n_nodes, cfg.n_edges, cfg.n, cfg.state_dim, cfg.node_dim
+    Pp = T + 1
+    SF, SI = float("nan"), -77777
+    full = {}
+
+    def guarded(key, shape, dtype):
+        t = torch.full((b + 2,) + tuple(shape), SI if dtype == torch.int32 else SF, dtype=dtype, device="cuda")
+        full[key] = t
+        return t[1:b + 1]
+
+    rec = dict(nodes=guarded("nodes", (Pp, N, nd), torch.float32), edges=guarded("edges", (Pp, E, 4), torch.float32),
+               states=guarded("states", (Pp, N, sd), torch.float32),
+               receivers=guarded("receivers", (Pp, E), torch.int32), senders=guarded("senders", (Pp, E), torch.int32),
+               node_type=guarded("node_type", (Pp, N), torch.int32), n_node=guarded("n_node", (Pp,), torch.int32),
+               n_edge=guarded("n_edge", (Pp,), torch.int32))
+    for k in rec:
+        rec[k][:, 0] = dev(g0[k])
+    rnn = guarded("rnn", (Pp, n, 64), torch.float32)
+    rnn[:, 0] = 0.0
+    actions = guarded("actions", (T, n, 2), torch.float32)
+    log_pis = guarded("log_pis", (T, n), torch.float32)
+    rewards = guarded("rewards", (T,), torch.float32)
+    costs = guarded("costs", (T, n, 2), torch.float32)
+    agent_ws = torch.zeros((2, b, n, sd), dtype=torch.float32, device="cuda")
+    agent_ws[0] = dev(agent)
+    hits_ws, obst, rays_d = None, None, None
+    if cfg.is_lidar and cfg.n_obs > 0:
+        hits_ws = dev(env_np.graph_slices(cfg, g0)[2])
+        obst = dev(util.obs_record(obstacles))
+        rays_d = dev(rays)
+    elif cfg.n_obs > 0:
+        obst = dev(mpe_obs)
+    e_d, goal_d = dev(eps), dev(goal)
+    buf = _lib.DgppoRolloutBuffers(p(rec["nodes"]), p(rec["edges"]), p(rec["states"]), p(rec["receivers"]),
+                                   p(rec["senders"]), p(rec["node_type"]), p(rec["n_node"]), p(rec["n_edge"]),
+                                   p(rnn), p(e_d), p(actions), p(log_pis), p(rewards), p(costs), p(agent_ws),
+                                   p(hits_ws), p(goal_d), p(obst), p(rays_d))
+    cc = util.c_cfg(cfg)
+    rc = _lib.lib().dgppo_rollout(stream(), C.byref(cc), C.byref(nc), p(packed), C.byref(buf), T, b, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for key, t in full.items():
+        h = t.cpu().numpy()
+        for guard in (h[0], h[-1]):
+            if h.dtype == np.int32:
+                assert (guard == SI).all(), f"{key}: guard environment overwritten"
+            else:
+                assert np.isnan(guard).all(), f"{key}: guard environment overwritten"
+        inner = h[1:-1]
+        if h.dtype == np.int32:
+            assert (inner != SI).all(), f"{key}: elements left unwritten"
+        else:
+            assert not np.isnan(inner).any(), f"{key}: elements left unwritten (or NaN produced)"
