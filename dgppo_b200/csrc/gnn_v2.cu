@@ -6,14 +6,16 @@
 // into two persistent kernels whose weights are loaded ONCE per CTA into shared
 // memory and stay there for every tile:
 //
-//   gnn_layers_kernel : GNN layers for a tile of G graphs (G*n <= 32 agent rows);
-//                       smem = GNN weights (~99 KB) + node/row activations.
-//                       Output: agent embeddings (rows x 64) into the caller's
-//                       rnn_out buffer, used as scratch.
-//   head_kernel       : head MLP + LayerNorm + GRU + tails for a tile of 64 rows;
-//                       smem = head/GRU/tail weights (~148 KB) + activations.
-//                       Reads the embeddings back from rnn_out, then overwrites
-//                       them with the new GRU carry.
+//   gnn_layers_kernel     : GNN layers for a tile of G graphs (G*n <= 16 agent rows),
+//                           256 threads, 2 CTAs per SM; smem = GNN weights (~57 KB) +
+//                           node/row activations.  Output: agent embeddings (rows x 64)
+//                           into the caller's rnn_out buffer, used as scratch.
+//   gnn_layers_big_kernel : the same for n > 16: one graph per tile, rows in chunks of 16,
+//                           attention over compacted lists of live slots.
+//   head_kernel_wide      : head MLP + LayerNorm + GRU + tails for a tile of 128 rows
+//                           (head_kernel<WR>: 64 rows); smem = head/GRU/tail weights
+//                           (~148 KB) + activations.  Reads the embeddings back from
+//                           rnn_out, then overwrites them with the new GRU carry.
 //
 // Same arithmetic as v1 (GNN regrouping); attention is parallelised
 // over (row, head, edge slot) instead of (row, head).
