@@ -124,6 +124,19 @@ struct GnnV2Plan {
   size_t head_smem_bytes;
 };
 
+// GRU gate activations of head_kernel_wide on the SFU (ex2.approx / rcp.approx): absolute error
+// below 3e-7 on outputs in (0, 1) / (-1, 1), inside the fp32 tolerance of the path (rtol 1e-5).
+__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) {
+  const float ax = fminf(fabsf(x), 15.f);                  // tanh(15) == 1 in fp32; keeps exp finite
+  const float t = 1.f - __fdividef(2.f, __expf(2.f * ax) + 1.f);
+  return copysignf(t, x);
+}
+
+// exp of a non-positive softmax argument: ex2.approx(x * log2 e).  Relative error <= 2^-22 + |x| 2^-24,
+// i.e. below 1e-6 wherever exp(x) still matters; the weights that dominate the sum have x near 0.
+__device__ __forceinline__ float softmax_exp(float x) { return __expf(x); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -204,7 +217,7 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
     for (int h = 0; h < H; ++h) {
       l[h] = 0.f;
 #pragma unroll
-      for (int j = 0; j < J; ++j) { sc[j][h] = (sv[j] >= 0) ? expf(sc[j][h] - mx[h]) : 0.f; l[h] += sc[j][h]; }
+      for (int j = 0; j < J; ++j) { sc[j][h] = (sv[j] >= 0) ? softmax_exp(sc[j][h] - mx[h]) : 0.f; l[h] += sc[j][h]; }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -213,7 +226,7 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      const float inv_l = (l[h] > 0.f) ? 1.f / l[h] : 0.f;
+      const float inv_l = (l[h] > 0.f) ? __fdividef(1.f, l[h]) : 0.f;
 #pragma unroll
       for (int j = 0; j < J; ++j) sc[j][h] *= inv_l;
     }
@@ -569,7 +582,7 @@ __device__ __forceinline__ void attention_row_big(int r, bool live, int lane, co
     ef_next = edge_of(p + 32);                        // in flight while this chunk is processed
     if (p < count) {
       float4 a = al[p];
-      a.x = expf(a.x - mx[0]); a.y = expf(a.y - mx[1]); a.z = expf(a.z - mx[2]);
+      a.x = softmax_exp(a.x - mx[0]); a.y = softmax_exp(a.y - mx[1]); a.z = softmax_exp(a.z - mx[2]);
       al[p] = a;
       l[0] += a.x; l[1] += a.y; l[2] += a.z;
       v[0] = fmaf(a.x, ef.x, v[0]); v[1] = fmaf(a.x, ef.y, v[1]); v[2] = fmaf(a.x, ef.z, v[2]); v[3] = fmaf(a.x, ef.w, v[3]);
@@ -579,7 +592,7 @@ __device__ __forceinline__ void attention_row_big(int r, bool live, int lane, co
   }
   float inv_l[H];
 #pragma unroll
-  for (int h = 0; h < H; ++h) { l[h] = warp_sum(l[h]); inv_l[h] = (l[h] > 0.f) ? 1.f / l[h] : 0.f; }
+  for (int h = 0; h < H; ++h) { l[h] = warp_sum(l[h]); inv_l[h] = (l[h] > 0.f) ? __fdividef(1.f, l[h]) : 0.f; }
   warp_reduce16(v, lane);
   __syncwarp();
   {
@@ -1122,9 +1135,9 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
           const int p = i >> 1;
           const float sr = (i & 1) ? ar[p][j].y : ar[p][j].x, sz = (i & 1) ? az[p][j].y : az[p][j].x;
           const float sn = (i & 1) ? an[p][j].y : an[p][j].x, sh = (i & 1) ? ahn[p][j].y : ahn[p][j].x;
-          const float rgate = sigmoidf_(sr + bir);
-          const float zgate = sigmoidf_(sz + biz);
-          const float cand = tanhf(sn + bin + rgate * (sh + bh));
+          const float rgate = gate_sigmoid(sr + bir);
+          const float zgate = gate_sigmoid(sz + biz);
+          const float cand = gate_tanh(sn + bin + rgate * (sh + bh));
           hn[i][j] = (1.f - zgate) * cand + zgate * b1[c * R3S + r0 + i];   // previous carry (parked in b1)
         }
       }
