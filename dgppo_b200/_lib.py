@@ -36,7 +36,7 @@ class DgppoNetCfg(C.Structure):
 class DgppoNetLayout(C.Structure):
     _fields_ = ([(k, C.c_int32 * 2) for k in ("wqk", "wagg", "wu", "bu", "wq", "bq", "wkt", "in_dim", "out_dim")] +
                 [(k, C.c_int32) for k in ("d0w", "d0b", "ln0s", "ln0b", "d1w", "d1b", "ln1s", "ln1b",
-                                          "wi", "bi", "wh", "bhn", "scale_w", "scale_b", "out_w", "out_b",
+                                          "wi", "bi", "wh", "bhn", "out_w", "out_b",
                                           "total")])
 
 
@@ -100,7 +100,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(h, name)
             fn.restype, fn.argtypes = res, args
-        if h.dgppo_abi_version() != 1:
+        if h.dgppo_abi_version() != 2:
             raise DgppoLibraryError("libdgppo_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -175,11 +175,15 @@ def pack_params(tree: Dict, cfg: _lib.DgppoNetCfg) -> np.ndarray:
     out_w = np.zeros((HID, 4), np.float32)
     out_b = np.zeros(4, np.float32)
     if policy:
-        put(L.scale_w, p["ScaleHid"]["kernel"]); put(L.scale_b, p["ScaleHid"]["bias"])
         nu = cfg.n_out
         out_w[:, :nu] = _np(p["OutputDenseMean"]["kernel"]); out_b[:nu] = _np(p["OutputDenseMean"]["bias"])
         out_w[:, 2:2 + nu] = _np(p["OutputDenseStdTrans"]["kernel"])
         out_b[2:2 + nu] = _np(p["OutputDenseStdTrans"]["bias"])
+        # ScaleHid is a Dense without activation in front of the two output Denses (policy.py:66-70):
+        # fold it in, (x Ws + bs) Wo + bo = x (Ws Wo) + (bs Wo + bo); products in double, rounded once
+        ws, bs = _np(p["ScaleHid"]["kernel"]).astype(np.float64), _np(p["ScaleHid"]["bias"]).astype(np.float64)
+        out_b = (bs @ out_w.astype(np.float64) + out_b.astype(np.float64)).astype(np.float32)
+        out_w = (ws @ out_w.astype(np.float64)).astype(np.float32)
     else:
         out_w[:, :cfg.n_out] = _np(p["Dense_0"]["kernel"]); out_b[:cfg.n_out] = _np(p["Dense_0"]["bias"])
     put(L.out_w, out_w); put(L.out_b, out_b)

@@ -19,7 +19,7 @@ struct NetP {
   LayerP L[2];
   int n_layers, kind, n_out;
   const float *d0w, *d0b, *ln0s, *ln0b, *d1w, *d1b, *ln1s, *ln1b;
-  const float *wi, *bi, *wh, *bhn, *scale_w, *scale_b, *out_w, *out_b;
+  const float *wi, *bi, *wh, *bhn, *out_w, *out_b;
 };
 
 struct GnnArgs {

@@ -424,13 +424,7 @@ gnn_forward_kernel(NetP net, GnnArgs g, int m_cap) {
     }
 
     // ---- tails
-    const float* feat = y1;
-    if (net.kind == DGPPO_NET_POLICY) {
-      tile_gemm(y1, HID, RowPtr{net.scale_w, HID}, 1.f, nullptr, 0, RowPtr{nullptr, 0}, HID / 4,
-                StoreT{y0, net.scale_b, false});      // ScaleHid (policy.py:67)
-      __syncthreads();
-      feat = y0;
-    }
+    const float* feat = y1;                           // ScaleHid is folded into out_w at pack time
     tile_gemm(feat, HID, RowPtr{net.out_w, 4}, 1.f, nullptr, 0, RowPtr{nullptr, 0}, 1,
               StoreT{q, net.out_b, false});           // [4][RS]: mean0, mean1, std0, std1 | value cols
     __syncthreads();
@@ -473,8 +467,6 @@ static int fill_layout(const DgppoNetCfg* net, DgppoNetLayout* L) {
   L->d0w = take(64 * 64); L->d0b = take(64); L->ln0s = take(64); L->ln0b = take(64);
   L->d1w = take(64 * 64); L->d1b = take(64); L->ln1s = take(64); L->ln1b = take(64);
   L->wi = take(64 * 192); L->bi = take(192); L->wh = take(64 * 192); L->bhn = take(64);
-  if (net->kind == DGPPO_NET_POLICY) { L->scale_w = take(64 * 64); L->scale_b = take(64); }
-  else { L->scale_w = L->scale_b = -1; }
   L->out_w = take(64 * 4); L->out_b = take(4);
   for (int l = 0; l < 2; ++l) {                            // fallback-kernel blocks
     if (l >= net->n_layers) { L->wq[l] = L->bq[l] = L->wkt[l] = -1; continue; }
@@ -509,8 +501,6 @@ static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* n
   P.d0w = params + L.d0w; P.d0b = params + L.d0b; P.ln0s = params + L.ln0s; P.ln0b = params + L.ln0b;
   P.d1w = params + L.d1w; P.d1b = params + L.d1b; P.ln1s = params + L.ln1s; P.ln1b = params + L.ln1b;
   P.wi = params + L.wi; P.bi = params + L.bi; P.wh = params + L.wh; P.bhn = params + L.bhn;
-  P.scale_w = (L.scale_w >= 0) ? params + L.scale_w : nullptr;
-  P.scale_b = (L.scale_b >= 0) ? params + L.scale_b : nullptr;
   P.out_w = params + L.out_w; P.out_b = params + L.out_b;
 
   int dev = 0, sms = 148;

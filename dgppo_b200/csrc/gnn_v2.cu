@@ -882,7 +882,6 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
   const float *wi = wptr(net.wi), *bi = wptr(net.bi), *wh = wptr(net.wh), *bhn = wptr(net.bhn);
   const float *out_w = wptr(net.out_w), *out_b = wptr(net.out_b);
   const bool policy = net.kind == DGPPO_NET_POLICY;
-  const float *scale_w = policy ? wptr(net.scale_w) : nullptr, *scale_b = policy ? wptr(net.scale_b) : nullptr;
 
   const int n = g.n;
   const int nr = (net.kind == DGPPO_NET_VL) ? 1 : n;       // rows per graph
@@ -986,12 +985,7 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
       }
     }
     __syncwarp();
-    const float* feat = y1;
-    if (policy) {
-      warp_dense64<WR>(y1, scale_w, scale_b, y0, r0, lane);       // ScaleHid (policy.py:67)
-      __syncwarp();
-      feat = y0;
-    }
+    const float* feat = y1;                                       // ScaleHid is folded into out_w at pack time
     {   // out: [64] -> 4 columns; lane = (row, column)
       const int rr = lane >> 2, col = lane & 3;
       if (rr < WR) {
@@ -1041,7 +1035,6 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
   const float *wi = wptr(net.wi), *bi = wptr(net.bi), *wh = wptr(net.wh), *bhn = wptr(net.bhn);
   const float *out_w = wptr(net.out_w), *out_b = wptr(net.out_b);
   const bool policy = net.kind == DGPPO_NET_POLICY;
-  const float *scale_w = policy ? wptr(net.scale_w) : nullptr, *scale_b = policy ? wptr(net.scale_b) : nullptr;
 
   const int n = g.n;
   const int nr = (net.kind == DGPPO_NET_VL) ? 1 : n;       // rows per graph
@@ -1155,12 +1148,7 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
         if (i < rows) g.rnn_out[row_off(row0 + i) + c] = hn[i][j];
     }
     __syncwarp();
-    const float* feat = b0;
-    if (policy) {
-      warp_dense64<WR3, R3S>(b0, scale_w, scale_b, b1, r0, lane);   // ScaleHid (policy.py:67)
-      __syncwarp();
-      feat = b1;
-    }
+    const float* feat = b0;                                         // ScaleHid is folded into out_w at pack time
     {   // out: [64] -> 4 columns; lane = (row, column)
       const int rr = lane >> 2, col = lane & 3;
       float acc = out_b[col];

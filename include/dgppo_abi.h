@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DGPPO_ABI_VERSION 1
+#define DGPPO_ABI_VERSION 2
 
 /* negative error codes (positive values are cudaError_t) */
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
@@ -204,8 +204,10 @@ typedef struct DgppoNetCfg {
  * Head (mlp.py:14-30): d0w [64][64], d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b.
  * GRU (flax GRUCell): wi = [ir|iz|in].kernel (64,192), bi = their biases
  *   (192), wh = [hr|hz|hn].kernel (64,192), bhn = hn.bias (64).
- * Tail: policy: scale_w [64][64], scale_b = ScaleHid; out_w [64][4] =
- *   [OutputDenseMean | OutputDenseStdTrans] (n_out = 2), out_b [4].
+ * Tail: policy (policy.py:66-70): ScaleHid is a Dense WITHOUT activation feeding two Denses, so the
+ *   three are merged at pack time (products in double, rounded once):
+ *   out_w [64][4] = ScaleHid.kernel @ [OutputDenseMean.kernel | OutputDenseStdTrans.kernel] (n_out = 2),
+ *   out_b [4]     = ScaleHid.bias @ [Mean.kernel | StdTrans.kernel] + [Mean.bias | StdTrans.bias].
  *   value: out_w [64][4] = Dense_0.kernel zero-padded to 4 columns, out_b [4]. */
 typedef struct DgppoNetLayout {
   int32_t wqk[2], wagg[2], wu[2], bu[2];
@@ -213,7 +215,7 @@ typedef struct DgppoNetLayout {
   int32_t in_dim[2], out_dim[2];
   int32_t d0w, d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b;
   int32_t wi, bi, wh, bhn;
-  int32_t scale_w, scale_b, out_w, out_b;
+  int32_t out_w, out_b;
   int32_t total;      /* floats in the packed buffer */
 } DgppoNetLayout;
 
