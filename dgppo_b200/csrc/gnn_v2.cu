@@ -798,12 +798,12 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
 
 // ------------------------------------------------------------------ head
 // Each WARP owns 8 rows of the tile end to end (head MLP -> LayerNorm -> GRU ->
-// tails); lanes span the output columns {lane, lane + 32}.  The A operand (the
-// warp's 8 rows of one feature) is a warp-uniform 2 x LDS.128, the weight row a
-// conflict-free LDS.32 per column: 4-6 FFMA per shared-memory wavefront, and no
+// tails); lane l owns the output columns {2l, 2l + 1}.  The A operand (the
+// warp's 8 rows of one feature) is a warp-uniform 2 x LDS.128, the weight pair one
+// conflict-free LDS.64: 8 FFMA2 per three shared-memory instructions, and no
 // block-wide barrier inside the tile loop (warps never exchange data).
 
-// out[c][r0..r0+WR) = bias[c] + sum_k A[k][r0..r0+WR) * W[k][c]   for c = lane, lane + 32.
+// out[c][r0..r0+WR) = bias[c] + sum_k A[k][r0..r0+WR) * W[k][c]   for c = 2 lane, 2 lane + 1.
 // Packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2, new on sm_100): accumulators are (row 2p, row 2p+1)
 // pairs, the A float4 supplies the row pairs directly and only the two weights are duplicated, so
 // each k costs 2 MOV + WR FFMA2 instead of 2*WR FFMA (B200: 65.9 vs 42.4 TFLOP/s measured,
@@ -822,8 +822,8 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
       const float4 a = *reinterpret_cast<const float4*>(A + k * STR + r0 + 4 * i4);
       ap[2 * i4] = make_float2(a.x, a.y); ap[2 * i4 + 1] = make_float2(a.z, a.w);
     }
-    const float w0 = W[k * HID + lane], w1 = W[k * HID + lane + 32];
-    const float2 w0d = make_float2(w0, w0), w1d = make_float2(w1, w1);
+    const float2 w = *reinterpret_cast<const float2*>(W + k * HID + 2 * lane);
+    const float2 w0d = make_float2(w.x, w.x), w1d = make_float2(w.y, w.y);
 #pragma unroll
     for (int p = 0; p < WR / 2; ++p) {
       acc[p][0] = __ffma2_rn(ap[p], w0d, acc[p][0]);
@@ -832,7 +832,7 @@ __device__ __forceinline__ void warp_dense64(const float* A, const float* W, con
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const int c = lane + 32 * j;
+    const int c = 2 * lane + j;
     const float bj = bias[c];
 #pragma unroll
     for (int i4 = 0; i4 < WR / 4; ++i4)
@@ -924,7 +924,7 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
     __syncwarp();
     warp_layernorm_relu<WR>(y0, ln1s, ln1b, r0, lane);
     __syncwarp();
-    // GRU cell (flax GRUCell; rnn.py:19-21): 8 rows x units {lane, lane+32} x 3 gates
+    // GRU cell (flax GRUCell; rnn.py:19-21): 8 rows x units {2 lane, 2 lane + 1} x 3 gates
     {
       float2 ai[3][WR / 2][2], ah[3][WR / 2][2];      // (row 2p, row 2p+1) pairs, see warp_dense64
 #pragma unroll
@@ -946,10 +946,10 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
         }
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const float wi0 = wi[k * 192 + t * 64 + lane], wi1 = wi[k * 192 + t * 64 + lane + 32];
-          const float wh0 = wh[k * 192 + t * 64 + lane], wh1 = wh[k * 192 + t * 64 + lane + 32];
-          const float2 wi0d = make_float2(wi0, wi0), wi1d = make_float2(wi1, wi1);
-          const float2 wh0d = make_float2(wh0, wh0), wh1d = make_float2(wh1, wh1);
+          const float2 wiv = *reinterpret_cast<const float2*>(wi + k * 192 + t * 64 + 2 * lane);
+          const float2 whv = *reinterpret_cast<const float2*>(wh + k * 192 + t * 64 + 2 * lane);
+          const float2 wi0d = make_float2(wiv.x, wiv.x), wi1d = make_float2(wiv.y, wiv.y);
+          const float2 wh0d = make_float2(whv.x, whv.x), wh1d = make_float2(whv.y, whv.y);
 #pragma unroll
           for (int p = 0; p < WR / 2; ++p) {
             ai[t][p][0] = __ffma2_rn(xp[p], wi0d, ai[t][p][0]); ai[t][p][1] = __ffma2_rn(xp[p], wi1d, ai[t][p][1]);
@@ -959,7 +959,7 @@ head_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ params)
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int c = lane + 32 * j;
+        const int c = 2 * lane + j;
         const float bir = bi[c], biz = bi[64 + c], bin = bi[128 + c], bh = bhn[c];
         float hn[WR];
 #pragma unroll
@@ -1060,7 +1060,8 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
         const size_t off = row_off(row0 + i);
         cp_async4(b0 + lane * R3S + r0 + i, g.rnn_out + off + lane);
         cp_async4(b0 + (lane + 32) * R3S + r0 + i, g.rnn_out + off + lane + 32);
-        hreg[i][0] = __ldg(g.rnn_in + off + lane); hreg[i][1] = __ldg(g.rnn_in + off + lane + 32);
+        const float2 hv = __ldg(reinterpret_cast<const float2*>(g.rnn_in + off) + lane);   // units 2 lane, 2 lane + 1
+        hreg[i][0] = hv.x; hreg[i][1] = hv.y;
       } else {
         b0[lane * R3S + r0 + i] = 0.f; b0[(lane + 32) * R3S + r0 + i] = 0.f;
         hreg[i][0] = 0.f; hreg[i][1] = 0.f;
@@ -1080,10 +1081,10 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int i4 = 0; i4 < WR3 / 4; ++i4)
-        *reinterpret_cast<float4*>(b1 + (lane + 32 * j) * R3S + r0 + 4 * i4) =
+        *reinterpret_cast<float4*>(b1 + (2 * lane + j) * R3S + r0 + 4 * i4) =
             make_float4(hreg[4 * i4][j], hreg[4 * i4 + 1][j], hreg[4 * i4 + 2][j], hreg[4 * i4 + 3][j]);
     __syncwarp();
-    // GRU cell (flax GRUCell; rnn.py:19-21): x = b0, h = b1; units {lane, lane + 32}
+    // GRU cell (flax GRUCell; rnn.py:19-21): x = b0, h = b1; units {2 lane, 2 lane + 1} (weights: LDS.64)
     float hn[WR3][2];
     {
       float2 ar[WR3 / 2][2], az[WR3 / 2][2], an[WR3 / 2][2], ahn[WR3 / 2][2];
@@ -1101,15 +1102,16 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
           xp[2 * i4] = make_float2(xa.x, xa.y); xp[2 * i4 + 1] = make_float2(xa.z, xa.w);
           hp[2 * i4] = make_float2(ha.x, ha.y); hp[2 * i4 + 1] = make_float2(ha.z, ha.w);
         }
-        const float* wik = wi + k * 192 + lane;
-        const float* whk = wh + k * 192 + lane;
+        const float2* wik = reinterpret_cast<const float2*>(wi + k * 192) + lane;
+        const float2* whk = reinterpret_cast<const float2*>(wh + k * 192) + lane;
+        const float2 vir = wik[0], viz = wik[32], vin = wik[64], vhr = whk[0], vhz = whk[32], vhn = whk[64];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const float2 wir = make_float2(wik[32 * j], wik[32 * j]), whr = make_float2(whk[32 * j], whk[32 * j]);
-          const float2 wiz = make_float2(wik[64 + 32 * j], wik[64 + 32 * j]);
-          const float2 whz = make_float2(whk[64 + 32 * j], whk[64 + 32 * j]);
-          const float2 win = make_float2(wik[128 + 32 * j], wik[128 + 32 * j]);
-          const float2 whn = make_float2(whk[128 + 32 * j], whk[128 + 32 * j]);
+          const float sir = j ? vir.y : vir.x, siz = j ? viz.y : viz.x, sin_ = j ? vin.y : vin.x;
+          const float shr = j ? vhr.y : vhr.x, shz = j ? vhz.y : vhz.x, shn = j ? vhn.y : vhn.x;
+          const float2 wir = make_float2(sir, sir), whr = make_float2(shr, shr);
+          const float2 wiz = make_float2(siz, siz), whz = make_float2(shz, shz);
+          const float2 win = make_float2(sin_, sin_), whn = make_float2(shn, shn);
 #pragma unroll
           for (int p = 0; p < WR3 / 2; ++p) {
             ar[p][j] = __ffma2_rn(xp[p], wir, ar[p][j]); ar[p][j] = __ffma2_rn(hp[p], whr, ar[p][j]);
@@ -1121,7 +1123,7 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
       }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int c = lane + 32 * j;
+        const int c = 2 * lane + j;
         const float bir = bi[c], biz = bi[64 + c], bin = bi[128 + c], bh = bhn[c];
 #pragma unroll
         for (int i = 0; i < WR3; ++i) {
@@ -1138,15 +1140,16 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
     __syncwarp();                                                   // every lane is done reading b0 / b1
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int c = lane + 32 * j;
+      const int c = 2 * lane + j;
 #pragma unroll
       for (int i4 = 0; i4 < WR3 / 4; ++i4)
         *reinterpret_cast<float4*>(b0 + c * R3S + r0 + 4 * i4) =
             make_float4(hn[4 * i4][j], hn[4 * i4 + 1][j], hn[4 * i4 + 2][j], hn[4 * i4 + 3][j]);
-#pragma unroll
-      for (int i = 0; i < WR3; ++i)                                 // new carry, coalesced across lanes
-        if (i < rows) g.rnn_out[row_off(row0 + i) + c] = hn[i][j];
     }
+#pragma unroll
+    for (int i = 0; i < WR3; ++i)                                   // new carry, one float2 per lane (coalesced)
+      if (i < rows)
+        reinterpret_cast<float2*>(g.rnn_out + row_off(row0 + i))[lane] = make_float2(hn[i][0], hn[i][1]);
     __syncwarp();
     const float* feat = b0;                                         // ScaleHid is folded into out_w at pack time
     {   // out: [64] -> 4 columns; lane = (row, column)

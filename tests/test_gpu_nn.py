@@ -114,3 +114,27 @@ def test_vl_forward(name):
     v, h = util.k_value(cfg, nc, packed, g, rnn)
     _close(v, v32, v64, f"Vl {name}")
     _close(h, h32, h64, f"Vl carry {name}")
+
+
+@pytest.mark.parametrize("head", ["wr4", "wr8", "wide"])
+def test_head_kernel_variants(head, monkeypatch, kernel_generation):
+    """The 64-row head kernels (DGPPO_HEAD=wr4|wr8) stay selectable for A/B runs and as the plan when
+    the 128-row kernel's shared memory does not fit: same results as the default."""
+    if kernel_generation == "v1":
+        pytest.skip("DGPPO_HEAD only selects among the v2 head kernels")
+    monkeypatch.setenv("DGPPO_HEAD", head)
+    cfg = CONFIGS["C3"]
+    b = 37
+    g = _graph(cfg, b, 77)
+    tree = P.init_policy_params(cfg.node_dim, 4, 2, 2, seed=13, jitter=0.1, scale_final=1.0)
+    nc = P.net_cfg(_lib.NET_POLICY, cfg.node_dim, 4, 2, 2)
+    packed = P.pack_params(tree, nc)
+    rng = np.random.default_rng(5)
+    rnn = rng.standard_normal((b, cfg.n, 64)).astype(F) * 0.5
+    eps = rng.standard_normal((b, cfg.n, 2)).astype(F)
+    a32, lp32, h32, _ = nn_np.policy_forward(tree, g, rnn, cfg.n, eps, 2, np.float32)
+    a64, lp64, h64, _ = nn_np.policy_forward(tree, g, rnn, cfg.n, eps, 2, np.float64)
+    a, lp, h = util.k_policy(cfg, nc, packed, g, rnn, eps)
+    _close(h, h32, h64, f"rnn {head}")
+    _close(a, a32, a64, f"action {head}")
+    _close(lp, lp32, lp64, f"log_pi {head}")
