@@ -366,7 +366,9 @@ def run_gpu(args):
                        "l2": "record written per step is %.1f GB >> 126 MB L2" % (record.nbytes() / 1e9)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": args.steps * (5 * T + 2 if lidar else 4 * T + 1),   # policy = gnn_layers + head
+            # our kernels inside the timed region, per rollout: every env group (stream) launches
+            # T x {gnn_layers, head, env_step, [lidar], build_graph}; the reset graph adds [lidar] + build_graph
+            "gpu_launches": args.steps * (algo.rollout_chunks * (5 if lidar else 4) * T + (2 if lidar else 1)),
             "clocks": clocks,
             "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel_wide", "bound": "hbm",
                          "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
