@@ -92,7 +92,7 @@ class DGPPO(Algorithm):
         self._np_rng = np.random.default_rng(seed)
         self.last_prepass: Optional[dict] = None
         # independent env groups run on separate streams so env kernels overlap policy kernels
-        self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "2"))
+        self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "4"))
 
     # ------------------------------------------------------------ config / params
     @property
