@@ -36,7 +36,9 @@ struct GraphDims {
   int sd, nd, n_on, N, E, n_ag, n_ao, n, g;
 };
 
-__host__ __device__ inline bool is_lidar(int kind) { return kind != DGPPO_ENV_MPE_SPREAD; }
+__host__ __device__ inline bool is_mpe(int kind) { return kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_TARGET; }
+__host__ __device__ inline bool is_lidar(int kind) { return !is_mpe(kind); }
+__host__ __device__ inline bool is_spread(int kind) { return kind == DGPPO_ENV_LIDAR_SPREAD || kind == DGPPO_ENV_MPE_SPREAD; }
 __host__ __device__ inline bool is_bicycle(int kind) { return kind == DGPPO_ENV_LIDAR_BICYCLE_TARGET; }
 
 __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
@@ -48,7 +50,7 @@ __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
   const bool lid = is_lidar(c.kind);
   d.n_on = (c.n_obs > 0) ? (lid ? c.top_k * c.n_agents : c.n_obs) : 0;
   d.N = d.n + d.g + d.n_on + 1;
-  d.n_ag = (c.kind == DGPPO_ENV_LIDAR_SPREAD || c.kind == DGPPO_ENV_MPE_SPREAD) ? d.g : 1;
+  d.n_ag = is_spread(c.kind) ? d.g : 1;
   d.n_ao = (c.n_obs > 0) ? (lid ? c.top_k : c.n_obs) : 0;
   d.E = d.n * d.n + d.n * d.n_ag + d.n * d.n_ao;
   return d;
@@ -56,7 +58,7 @@ __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
 
 inline int check_env_cfg(const DgppoEnvCfg* c) {
   if (!c) return DGPPO_EINVAL;
-  if (c->kind < 0 || c->kind > 3) return DGPPO_ENOTSUP;
+  if (c->kind < 0 || c->kind > 4) return DGPPO_ENOTSUP;
   if (c->n_agents < 1 || c->n_obs < 0) return DGPPO_EINVAL;
   if (is_lidar(c->kind) && c->n_obs > 0) {
     if (c->n_rays < 1 || c->n_rays > 1024) return DGPPO_ENOTSUP;

@@ -31,7 +31,7 @@ static EnvConsts make_consts(const DgppoEnvCfg& c) {
     const float lo[5] = {0.f, 0.f, -1.f, -1.f, -0.5f}, hi[5] = {A, A, 1.f, 1.f, 0.5f};
     for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
   } else {
-    const float v = (c.kind == DGPPO_ENV_MPE_SPREAD) ? 1.0f : 0.5f;   // mpe/base.py:243-246 | lidar_env/base.py:273-276
+    const float v = is_mpe(c.kind) ? 1.0f : 0.5f;   // mpe/base.py:243-246 | lidar_env/base.py:273-276
     const float lo[5] = {0.f, 0.f, -v, -v, 0.f}, hi[5] = {A, A, v, v, 0.f};
     for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
   }
@@ -125,7 +125,7 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
 
   // reward (lidar_spread.py:35-52, lidar_target.py:35-52)
   const float* gl = goal + (size_t)env * n * sd;
-  const bool spread = (k.kind == DGPPO_ENV_LIDAR_SPREAD || k.kind == DGPPO_ENV_MPE_SPREAD);
+  const bool spread = is_spread(k.kind);
   for (int q = lane; q < n; q += 32) {
     const float gx = gl[q * sd], gy = gl[q * sd + 1];
     float d;

@@ -1,15 +1,17 @@
 """Environment registry and factory (dgppo/env/__init__.py:9-53).
 
-Only the environments on BASELINE.json's configs are registered:
-the other MPE / Lidar tasks and VMAS are outside this path.
+The environments on BASELINE.json's configs are registered plus
+MPETarget, the first of the "other env families through the same kernels" row
+(SURVEY.md 8f.4); the remaining MPE / Lidar tasks and VMAS are outside this path.
 """
 from typing import Optional
 
 from .base import MultiAgentEnv, StepResult
 from .envs import (LidarBicycleTarget, LidarEnv, LidarEnvState, LidarSpread, LidarTarget, MPE,
-                   MPEEnvState, MPESpread, Rectangle)
+                   MPEEnvState, MPESpread, MPETarget, Rectangle)
 
 ENV = {
+    "MPETarget": MPETarget,
     "MPESpread": MPESpread,
     "LidarSpread": LidarSpread,
     "LidarTarget": LidarTarget,

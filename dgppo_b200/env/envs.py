@@ -481,3 +481,12 @@ class MPESpread(MPE):
     PARAMS = {"car_radius": 0.05, "comm_radius": 0.5, "n_obs": 3, "obs_radius": 0.05,
               "default_area_size": 1.5, "dist2goal": 0.01}
     KIND = 3
+
+
+class MPETarget(MPE):
+    """dgppo/env/mpe/mpe_target.py: MPE dynamics / cost / obstacles with one paired goal per agent
+    (reward mpe_target.py:32-49, edge blocks :51-80).  First env family widened through the same
+    kernels."""
+    PARAMS = {"car_radius": 0.05, "comm_radius": 0.5, "n_obs": 3, "obs_radius": 0.05,
+              "default_area_size": 1.5, "dist2goal": 0.01}
+    KIND = 4

@@ -23,12 +23,14 @@ LIDAR_SPREAD = 0          # dgppo/env/lidar_env/lidar_spread.py
 LIDAR_TARGET = 1          # dgppo/env/lidar_env/lidar_target.py
 LIDAR_BICYCLE_TARGET = 2  # dgppo/env/lidar_env/lidar_bicycle_target.py
 MPE_SPREAD = 3            # dgppo/env/mpe/mpe_spread.py
+MPE_TARGET = 4            # dgppo/env/mpe/mpe_target.py
 
 KIND_BY_NAME = {
     "LidarSpread": LIDAR_SPREAD,
     "LidarTarget": LIDAR_TARGET,
     "LidarBicycleTarget": LIDAR_BICYCLE_TARGET,
     "MPESpread": MPE_SPREAD,
+    "MPETarget": MPE_TARGET,
 }
 
 
@@ -51,7 +53,7 @@ class EnvCfg:
 
     @property
     def is_lidar(self) -> bool:
-        return self.kind != MPE_SPREAD
+        return self.kind not in (MPE_SPREAD, MPE_TARGET)
 
     @property
     def is_bicycle(self) -> bool:
@@ -236,7 +238,7 @@ def state_lim(cfg: EnvCfg) -> Tuple[np.ndarray, np.ndarray]:
     A = cfg.area
     if cfg.is_bicycle:
         return np.array([0, 0, -1, -1, -0.5], F), np.array([A, A, 1, 1, 0.5], F)
-    if cfg.kind == MPE_SPREAD:
+    if not cfg.is_lidar:
         return np.array([0, 0, -1, -1], F), np.array([A, A, 1, 1], F)
     return np.array([0, 0, -0.5, -0.5], F), np.array([A, A, 0.5, 0.5], F)
 
@@ -475,7 +477,7 @@ def synthetic_states(cfg: EnvCfg, b: int, seed: int = 0):
         v = rng.uniform(-0.5, 0.5, (b, n, 1)).astype(F)
         agent = np.concatenate([pos, np.cos(th)[..., None], np.sin(th)[..., None], v], axis=-1).astype(F)
     else:
-        vmax = 1.0 if cfg.kind == MPE_SPREAD else 0.5
+        vmax = 1.0 if not cfg.is_lidar else 0.5
         vel = rng.uniform(-vmax, vmax, (b, n, 2)).astype(F)
         agent = np.concatenate([pos, vel], axis=-1).astype(F)
     goal = np.zeros((b, n, cfg.state_dim), F)

@@ -16,6 +16,7 @@ CASES = {
     "LidarBicycleTarget_n4_obs3": env_np.EnvCfg(env_np.LIDAR_BICYCLE_TARGET, n=4, n_obs=3),
     "MPESpread_n8_obs3": env_np.EnvCfg(env_np.MPE_SPREAD, n=8, n_obs=3),
     "LidarSpread_n4_obs0": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
+    "MPETarget_n6_obs3": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
 }
 
 

@@ -70,7 +70,7 @@ def _np_obstacles(rect):
 
 
 @pytest.mark.parametrize("env_id,n,obs", [("LidarSpread", 3, 3), ("LidarTarget", 4, 2), ("LidarBicycleTarget", 4, 3),
-                                          ("MPESpread", 5, 3)])
+                                          ("MPESpread", 5, 3), ("MPETarget", 6, 3)])
 def test_env_api_reset_step(env_id, n, obs):
     from dgppo_b200.env import make_env
     env = make_env(env_id, num_agents=n, num_obs=obs)

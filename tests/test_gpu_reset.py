@@ -18,6 +18,7 @@ CASES = {
     "LidarTarget": env_np.EnvCfg(env_np.LIDAR_TARGET, n=5, n_obs=2),
     "LidarBicycleTarget": env_np.EnvCfg(env_np.LIDAR_BICYCLE_TARGET, n=4, n_obs=3),
     "MPESpread": env_np.EnvCfg(env_np.MPE_SPREAD, n=8, n_obs=3),
+    "MPETarget": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
     "LidarSpread_noobs": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
     "crowded": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=24, n_obs=12),
 }

@@ -21,6 +21,7 @@ CONFIGS = {   # BASELINE.json configs at test sizes (b small), + edge cases
     "fullobs": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=6, n_obs=4, comm_radius=15.0),
     "one_agent": env_np.EnvCfg(env_np.LIDAR_TARGET, n=1, n_obs=1),
     "rays48": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=5, n_obs=3, n_rays=48, top_k=8),
+    "mpe_target": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
     # n > 16: the one-graph-per-tile GNN kernel (row chunks of 16, ragged last chunk)
     "n24": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=24, n_obs=5),
     "mpe20": env_np.EnvCfg(env_np.MPE_SPREAD, n=20, n_obs=3),

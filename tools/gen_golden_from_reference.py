@@ -31,6 +31,7 @@ CASES = {   # name -> (module, class, n_agents, n_obs, n_envs, n_steps)
     "LidarBicycleTarget_n4_obs3": ("dgppo.env.lidar_env.lidar_bicycle_target", "LidarBicycleTarget", 4, 3, 4, 5),
     "MPESpread_n8_obs3": ("dgppo.env.mpe.mpe_spread", "MPESpread", 8, 3, 4, 5),
     "LidarSpread_n4_obs0": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 4, 0, 3, 4),
+    "MPETarget_n6_obs3": ("dgppo.env.mpe.mpe_target", "MPETarget", 6, 3, 4, 5),
 }
 GRAPH_FIELDS = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
 
@@ -163,7 +164,10 @@ def run_nn():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]                      # optional: names of env cases to (re)generate
     for name, spec in CASES.items():
-        run_case(name, *spec)
-    run_gae()
-    run_nn()
+        if not only or name in only:
+            run_case(name, *spec)
+    if not only:
+        run_gae()
+        run_nn()
