@@ -40,6 +40,8 @@ class DgppoNetLayout(C.Structure):
                                           "total")])
 
 
+ABI_VERSION = 2        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
+
 _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 
 
@@ -100,7 +102,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(h, name)
             fn.restype, fn.argtypes = res, args
-        if h.dgppo_abi_version() != 2:
+        if h.dgppo_abi_version() != ABI_VERSION:
             raise DgppoLibraryError("libdgppo_b200.so ABI version mismatch")
         _lib = h
     return _lib

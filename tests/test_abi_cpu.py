@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libdgppo_b200.so does not export {s}"
     assert set(syms) == set(_lib.SIGNATURES), (set(syms) ^ set(_lib.SIGNATURES))
-    assert lib.dgppo_abi_version() == 2
+    assert lib.dgppo_abi_version() == _lib.ABI_VERSION == 2
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -104,3 +104,13 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.DgppoLibraryError):
         _lib.lib()
+
+
+def test_abi_version_is_one_number_everywhere():
+    """Header, library, ctypes mirror (and through it __graft_entry__.build()) agree on the ABI version."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "dgppo_abi.h")).read()
+    ver = int(re.search(r"#define\s+DGPPO_ABI_VERSION\s+(\d+)", hdr).group(1))
+    assert ver == _lib.ABI_VERSION == _lib.lib().dgppo_abi_version()
+    entry = open(os.path.join(root, "__graft_entry__.py")).read()
+    assert "_lib.ABI_VERSION" in entry and not re.search(r"dgppo_abi_version\(\)\s*==\s*\d", entry)
