@@ -1048,7 +1048,9 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
     return (((size_t)env * g.rnn_pitch + slot) * nr + i) * HID;
   };
 
-  for (long wt = (long)blockIdx.x * 16 + warp; wt < n_wtiles; wt += (long)gridDim.x * 16) {
+  // warp tiles are dealt round-robin over the CTAs (tile wt -> CTA wt % grid), so a partial last round
+  // thins out every SM evenly instead of leaving whole SMs idle
+  for (long wt = (long)warp * gridDim.x + blockIdx.x; wt < n_wtiles; wt += (long)gridDim.x * 16) {
     const long row0 = wt * WR3;
     const int rows = (int)min((long)WR3, total_rows - row0);
     __syncwarp();
@@ -1242,7 +1244,8 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   const bool want_wide = !hv || hv[0] == 'w' && hv[1] == 'i';
   if (want_wide && wide_smem <= 227 * 1024) {
     const long w_tiles = (total_rows + R3 - 1) / R3;
-    const int grid3 = w_tiles < sms ? (int)w_tiles : sms;
+    const int grid3 = w_tiles < sms ? (int)w_tiles : sms;      // no more CTAs than full 128-row tiles: spreading a
+                                                               // small batch over all SMs blocks the other streams
     err = cudaFuncSetAttribute(head_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem);
     if (err != cudaSuccess) return (int)err;
     head_kernel_wide<<<grid3, 512, wide_smem, st>>>(P, g, pl, params);
