@@ -326,32 +326,48 @@ build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
   __syncthreads();
 
   const size_t slot = (size_t)env * pitch;
-  // nodes (N, nd), states (N, sd), node_type (N): lidar_env/base.py:234-264
-  float* on_ = nodes + slot * N * nd;
-  for (int idx = threadIdx.x; idx < N * nd; idx += K3_THREADS) {
-    const int row = idx / nd, c = idx - row * nd;
-    float v = 0.f;
-    if (row < n)            v = (c < sd) ? sa[row * sd + c] : ((c == sd + 2) ? 1.f : 0.f);
-    else if (row < n + g)   v = (c < sd) ? sg[(row - n) * sd + c] : ((c == sd + 1) ? 1.f : 0.f);
-    else if (row < N - 1) {
-      const int o = row - n - g;
-      v = (c < ow && c < sd) ? so[o * ow + c] : ((c == sd) ? 1.f : 0.f);
-    }
-    on_[idx] = v;
-  }
+  // nodes (N, nd), states (N, sd), node_type (N): lidar_env/base.py:234-264.  One thread per node row:
+  // the state row goes straight to global (a float4 when sd == 4), the feature row
+  // [state | one-hot(obstacle, goal, agent)] is assembled in shared memory and copied out coalesced.
+  float* nb = so + d.n_on * ow;                  // [N][nd]
   float* os_ = states + slot * N * sd;
-  for (int idx = threadIdx.x; idx < N * sd; idx += K3_THREADS) {
-    const int row = idx / sd, c = idx - row * sd;
-    float v;
-    if (row < n)            v = sa[row * sd + c];
-    else if (row < n + g)   v = sg[(row - n) * sd + c];
-    else if (row < N - 1)   v = (c < ow) ? so[(row - n - g) * ow + c] : 0.f;
-    else                    v = -1.f;                        // utils/graph.py:217
-    os_[idx] = v;
-  }
   int* ot_ = node_type + slot * N;
-  for (int row = threadIdx.x; row < N; row += K3_THREADS)
-    ot_[row] = (row < n) ? 0 : ((row < n + g) ? 1 : ((row < N - 1) ? 2 : -1));
+  for (int row = threadIdx.x; row < N; row += K3_THREADS) {
+    float st[SD];
+    int type;
+    if (row < n) {
+      type = 0;
+#pragma unroll
+      for (int c = 0; c < SD; ++c) st[c] = sa[row * sd + c];
+    } else if (row < n + g) {
+      type = 1;
+#pragma unroll
+      for (int c = 0; c < SD; ++c) st[c] = sg[(row - n) * sd + c];
+    } else if (row < N - 1) {
+      type = 2;
+      const int o = row - n - g;
+#pragma unroll
+      for (int c = 0; c < SD; ++c) st[c] = (c < ow) ? so[o * ow + c] : 0.f;
+    } else {
+      type = -1;                                  // pad node: state -1 (utils/graph.py:217), features 0
+#pragma unroll
+      for (int c = 0; c < SD; ++c) st[c] = -1.f;
+    }
+    if (SD == 4) {
+      reinterpret_cast<float4*>(os_)[row] = make_float4(st[0], st[1], st[2], st[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < SD; ++c) os_[row * sd + c] = st[c];
+    }
+    ot_[row] = type;
+    float* f = nb + row * nd;
+#pragma unroll
+    for (int c = 0; c < SD; ++c) f[c] = (type >= 0) ? st[c] : 0.f;
+    f[sd] = (type == 2) ? 1.f : 0.f; f[sd + 1] = (type == 1) ? 1.f : 0.f; f[sd + 2] = (type == 0) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  float* on_ = nodes + slot * N * nd;
+  for (int idx = threadIdx.x; idx < N * nd; idx += K3_THREADS) on_[idx] = nb[idx];
   if (threadIdx.x == 0) {
     if (n_node) n_node[slot] = N;
     if (n_edge) n_edge[slot] = E;
@@ -459,7 +475,7 @@ extern "C" int dgppo_build_graph(void* stream, const DgppoEnvCfg* cfg, const flo
   const GraphDims d = graph_dims(*cfg);
   if (d.n_on > 0 && !obs_nodes) return DGPPO_EINVAL;
   const int ow = is_lidar(cfg->kind) ? 2 : 4;
-  const size_t smem = (size_t)(d.n * d.sd + d.g * d.sd + (d.n + d.g) * 4 + d.n_on * ow) * sizeof(float);
+  const size_t smem = (size_t)(d.n * d.sd + d.g * d.sd + (d.n + d.g) * 4 + d.n_on * ow + d.N * d.nd) * sizeof(float);
   if (smem > 48 * 1024) return DGPPO_ENOTSUP;
   if (d.sd == 5)
     build_graph_kernel<5><<<b, K3_THREADS, smem, (cudaStream_t)stream>>>(
