@@ -187,6 +187,36 @@ __device__ __forceinline__ float lidar_slot_literal(float dx12, float dy12, floa
   return fadd(fmul(vf, alpha), fmul(fsub(1.f, vf), 1e6f));
 }
 
+// A near edge for one ray.  Three outcomes, decided without dividing:
+//   clearly invalid  (alpha or beta certainly outside [0, 1], see lidar_slot_literal): the slot
+//       contributes 1e6, which never changes the running minimum: nothing to do;
+//   clearly valid    (1e-30 < n < 0.9999 |det| for both numerators, taken over the positive
+//       denominator |det|, 1e-7 <= |det| <= 1e7): both rounded quotients lie strictly inside
+//       (0, 1), the slot contributes exactly alpha = RN(na / det).  Division is monotonic, so the
+//       minimum over such slots is RN of the smallest FRACTION: fractions are compared exactly
+//       (products of two floats as head + FMA tail) and only the winner is divided, once per ray;
+//   anything else    (borderline, det == 0 / NaN / clipped): the literal arithmetic.
+__device__ __forceinline__ void lidar_slot_near(float dx12, float dy12, float dx43, float dy43, float dx13,
+                                                float dy13, float na, float det_raw,
+                                                float& amin, float& best_num, float& best_den) {
+  const float ad = fabsf(det_raw);
+  const float nb = fadd(fmul(-dy12, dx13), fmul(dx12, dy13));
+  const bool neg = det_raw < 0.f;
+  const float an = neg ? -na : na, bn = neg ? -nb : nb;      // numerators over the denominator ad > 0
+  const bool regular = (ad >= 1e-7f) && (ad <= 1e7f);        // false for 0 and NaN; sign * clip is the identity here
+  const float hi = 1.0001f * ad, lo = 0.9999f * ad;
+  const bool out = (an > hi) || (an < -1e-30f) || (bn > hi) || (bn < -1e-30f);
+  const bool in = (an > 1e-30f) && (an < lo) && (bn > 1e-30f) && (bn < lo);
+  if (regular && in) {
+    // an / ad < best_num / best_den  <=>  an * best_den < best_num * ad   (all positive; exact)
+    const float p1 = __fmul_rn(an, best_den), e1 = __fmaf_rn(an, best_den, -p1);
+    const float p2 = __fmul_rn(best_num, ad), e2 = __fmaf_rn(best_num, ad, -p2);
+    if (p1 < p2 || (p1 == p2 && e1 < e2)) { best_num = an; best_den = ad; }
+  } else if (!(regular && out)) {
+    amin = nanmin(amin, lidar_slot_literal(dx12, dy12, dx43, dy43, dx13, dy13, na, det_raw));
+  }
+}
+
 __global__ void __launch_bounds__(K2_WARPS * 32)
 lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ obstacles,
              const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd) {
@@ -249,6 +279,7 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
     const float x2 = fadd(x1, ray_dirs[2 * r]), y2 = fadd(y1, ray_dirs[2 * r + 1]);
     const float dx12 = fsub(x1, x2), dy12 = fsub(y1, y2);
     float amin = 1e6f;                                  // every invalid slot contributes exactly 1e6
+    float best_num = 1.f, best_den = 0.f;               // smallest clearly-valid alpha as a fraction (+inf)
     for (int e = 0; e < ne; ++e) {
       const float4 g = ed[e];
       const float det = fsub(fmul(dx12, g.y), fmul(dy12, g.x));
@@ -258,9 +289,10 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
         if (!(fabsf(det) >= 1e-7f))
           amin = nanmin(amin, lidar_slot_literal(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det));
       } else {
-        amin = nanmin(amin, lidar_slot_literal(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det));
+        lidar_slot_near(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det, amin, best_num, best_den);
       }
     }
+    if (best_den != 0.f) amin = nanmin(amin, fdiv(best_num, best_den));
     const float a = fmul(amin, keep);                      // env/utils.py:129
     // alpha is +0, positive or NaN: its bit pattern orders like the value; NaN sorts last;
     // the ray index in the low bits makes the order total and stable (jnp.argsort, env/utils.py:132)
