@@ -154,12 +154,14 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
 // ------------------------------------------------------------------- K2
 // One warp per (environment, agent).
 //   phase 1  lane = obstacle edge: the ray-independent terms of the 2x2 solve
-//            (edge vector, agent - corner, numerator of alpha) and a conservative
-//            "edge farther than the sensing range" flag go to the warp's smem;
-//   phase 2  lane = ray: loop over the edges.  A far edge can only matter when the
-//            ray is (numerically) parallel to it, so it costs one determinant;
-//            a near edge runs the literal arithmetic of obstacle.py:82-104 behind a
-//            division-free early-out;
+//            (edge vector, agent - corner, numerator of alpha) go to the warp's smem,
+//            edges within the sensing range packed to the front, the others to the back
+//            (conservative distance test);
+//   phase 2  lane = ray: a far edge can only matter when the ray is (numerically) parallel
+//            to it, so it costs one determinant; a near edge is classified without dividing
+//            (lidar_slot_near): clearly invalid -> nothing, clearly valid -> exact fraction
+//            minimum (one division per ray at the end), borderline -> the literal arithmetic
+//            of obstacle.py:82-104;
 //   phase 3  stable top-k by counting rank over 64-bit (alpha bits, ray) keys.
 // Every value that reaches the output is produced by the same individually
 // rounded operations as the reference expression (bit-exact vs the oracle).
@@ -230,7 +232,7 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   float* base = smem + (size_t)warp * per_warp;
   float4* ed = reinterpret_cast<float4*>(base);                 // [ne] (dx43, dy43, dx13, dy13)
   float* nav = base + 4 * ne;                                   // [ne] numerator of alpha
-  float* farf = nav + ne;                                       // [ne] 1 = edge beyond the sensing range
+  float* farf = nav + ne;                                       // [ne] spare (keeps the launcher's layout)
   unsigned long long* key = reinterpret_cast<unsigned long long*>(farf + ((ne + 3) & ~3));   // [R]
   float* hx = reinterpret_cast<float*>(key + R);                // [R]
   float* hy = hx + R;
@@ -254,23 +256,38 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   in_any = __any_sync(0xffffffffu, in_any);
   const float keep = fsub(1.f, in_any ? 1.f : 0.f);
 
-  // ---- phase 1: per-edge terms
+  // ---- phase 1: per-edge terms; near edges are packed to the front of the warp's list, far edges
+  //      (beyond the sensing range) to the back, so phase 2 runs two branch-free loops
   const float reach = k.R * 1.002f + 1e-4f;            // a valid hit lies within comm_radius of the agent
-  for (int e = lane; e < ne; e += 32) {
-    const int o = e >> 2, q = e & 3;
-    const float* pts = ob + o * DGPPO_OBS_STRIDE + 8;
-    const float x3 = pts[2 * q], y3 = pts[2 * q + 1];
-    const float x4 = pts[2 * ((q + 3) & 3)], y4 = pts[2 * ((q + 3) & 3) + 1];
-    const float dx43 = fsub(x4, x3), dy43 = fsub(y4, y3);
-    const float dx13 = fsub(x1, x3), dy13 = fsub(y1, y3);
-    ed[e] = make_float4(dx43, dy43, dx13, dy13);
-    nav[e] = fsub(fmul(dy43, dx13), fmul(dx43, dy13));
-    // distance agent -> segment (approximate arithmetic; only used with a safety margin)
-    const float l2 = dx43 * dx43 + dy43 * dy43;
-    float t = (l2 > 0.f) ? (dx13 * dx43 + dy13 * dy43) / l2 : 0.f;
-    t = fminf(fmaxf(t, 0.f), 1.f);
-    const float cx = dx13 - t * dx43, cy = dy13 - t * dy43;
-    farf[e] = (cx * cx + cy * cy > reach * reach) ? 1.f : 0.f;
+  int n_near = 0, n_far = 0;
+  for (int e0 = 0; e0 < ne; e0 += 32) {
+    const int e = e0 + lane;
+    const bool act = e < ne;
+    float dx43 = 0.f, dy43 = 0.f, dx13 = 0.f, dy13 = 0.f;
+    bool far = false;
+    if (act) {
+      const int o = e >> 2, q = e & 3;
+      const float* pts = ob + o * DGPPO_OBS_STRIDE + 8;
+      const float x3 = pts[2 * q], y3 = pts[2 * q + 1];
+      const float x4 = pts[2 * ((q + 3) & 3)], y4 = pts[2 * ((q + 3) & 3) + 1];
+      dx43 = fsub(x4, x3); dy43 = fsub(y4, y3);
+      dx13 = fsub(x1, x3); dy13 = fsub(y1, y3);
+      // distance agent -> segment (approximate arithmetic; only used with a safety margin)
+      const float l2 = dx43 * dx43 + dy43 * dy43;
+      float t = (l2 > 0.f) ? (dx13 * dx43 + dy13 * dy43) / l2 : 0.f;
+      t = fminf(fmaxf(t, 0.f), 1.f);
+      const float cx = dx13 - t * dx43, cy = dy13 - t * dy43;
+      far = cx * cx + cy * cy > reach * reach;
+    }
+    const unsigned m_near = __ballot_sync(0xffffffffu, act && !far);
+    const unsigned m_far = __ballot_sync(0xffffffffu, act && far);
+    if (act) {
+      const unsigned lt = (1u << lane) - 1u;
+      const int p = far ? ne - 1 - (n_far + __popc(m_far & lt)) : n_near + __popc(m_near & lt);
+      ed[p] = make_float4(dx43, dy43, dx13, dy13);
+      nav[p] = fsub(fmul(dy43, dx13), fmul(dx43, dy13));
+    }
+    n_near += __popc(m_near); n_far += __popc(m_far);
   }
   __syncwarp();
 
@@ -280,16 +297,19 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
     const float dx12 = fsub(x1, x2), dy12 = fsub(y1, y2);
     float amin = 1e6f;                                  // every invalid slot contributes exactly 1e6
     float best_num = 1.f, best_den = 0.f;               // smallest clearly-valid alpha as a fraction (+inf)
-    for (int e = 0; e < ne; ++e) {
+    for (int e = 0; e < n_near; ++e) {
       const float4 g = ed[e];
       const float det = fsub(fmul(dx12, g.y), fmul(dy12, g.x));
-      if (farf[e] != 0.f) {                             // warp-uniform branch
-        // beyond reach: a regular solve cannot be valid; only a (near-)parallel ray, whose
-        // determinant is clipped / zero, still has to go through the literal arithmetic
-        if (!(fabsf(det) >= 1e-7f))
-          amin = nanmin(amin, lidar_slot_literal(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det));
-      } else {
-        lidar_slot_near(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det, amin, best_num, best_den);
+      lidar_slot_near(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det, amin, best_num, best_den);
+    }
+    for (int e = n_near; e < ne; ++e) {
+      // beyond reach: a regular solve cannot be valid; only a (near-)parallel ray, whose
+      // determinant is clipped / zero, still has to go through the literal arithmetic
+      const float2 g2 = *reinterpret_cast<const float2*>(&ed[e]);
+      const float det = fsub(fmul(dx12, g2.y), fmul(dy12, g2.x));
+      if (!(fabsf(det) >= 1e-7f)) {
+        const float4 g = ed[e];
+        amin = nanmin(amin, lidar_slot_literal(dx12, dy12, g.x, g.y, g.z, g.w, nav[e], det));
       }
     }
     if (best_den != 0.f) amin = nanmin(amin, fdiv(best_num, best_den));
