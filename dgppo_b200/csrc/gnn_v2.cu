@@ -430,18 +430,34 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       if (!last) {                          // non-agent nodes that send in the next layer (all threads)
         const int nn = nodes_per - n;
         for (int gl = 0; gl < gcount; ++gl) {
-          for (int idx = threadIdx.x; idx < nn * 8; idx += nth) {
-            const int s = gl * nodes_per + n + (idx >> 3), c0 = (idx & 7) * 4;
+          // one (node, 8 output columns) item per thread; layer 0 only: X = x0, rows of X0S = 8 floats
+          // (a non-final layer is 32 wide: gnn.py:136, dgppo_net_layout)
+          for (int idx = threadIdx.x; idx < nn * 4; idx += nth) {
+            const int s = gl * nodes_per + n + (idx >> 2), c0 = (idx & 3) * 8;
             if (!nflag[s]) continue;
-            const float* x = X + (size_t)s * XS;
-            float a0 = bu[c0], a1 = bu[c0 + 1], a2 = bu[c0 + 2], a3 = bu[c0 + 3];
-            for (int c = 0; c < IN; ++c) {
-              const float xv = x[c];
-              const float4 w = *reinterpret_cast<const float4*>(wu + c * D + c0);
-              a0 = fmaf(xv, w.x, a0); a1 = fmaf(xv, w.y, a1); a2 = fmaf(xv, w.z, a2); a3 = fmaf(xv, w.w, a3);
+            const float4 xa = *reinterpret_cast<const float4*>(x0 + (size_t)s * X0S);
+            const float4 xb = *reinterpret_cast<const float4*>(x0 + (size_t)s * X0S + 4);
+            const float xs[X0S] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            float2 acc[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[p] = make_float2(bu[c0 + 2 * p], bu[c0 + 2 * p + 1]);
+#pragma unroll
+            for (int c = 0; c < X0S; ++c) {
+              if (c < IN) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wu + c * D + c0);
+                const float4 w1 = *reinterpret_cast<const float4*>(wu + c * D + c0 + 4);
+                const float2 xd = make_float2(xs[c], xs[c]);
+                acc[0] = __ffma2_rn(xd, make_float2(w0.x, w0.y), acc[0]);
+                acc[1] = __ffma2_rn(xd, make_float2(w0.z, w0.w), acc[1]);
+                acc[2] = __ffma2_rn(xd, make_float2(w1.x, w1.y), acc[2]);
+                acc[3] = __ffma2_rn(xd, make_float2(w1.z, w1.w), acc[3]);
+              }
             }
-            *reinterpret_cast<float4*>(x1 + (size_t)s * X1S + c0) =
-                make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+            float* dst = x1 + (size_t)s * X1S + c0;
+            *reinterpret_cast<float4*>(dst) =
+                make_float4(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f), fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f));
+            *reinterpret_cast<float4*>(dst + 4) =
+                make_float4(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f), fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f));
           }
         }
       }
