@@ -25,6 +25,7 @@ import torch
 
 from .. import _lib
 from ..env.base import MultiAgentEnv, ptr, require_cuda, stream_ptr
+from ..env.envs import check_reset
 from ..trainer.data import Rollout
 from ..trainer.rollout import RNN_DIM, run_rollout, run_rollout_chunked
 from ..utils.graph import GraphsTuple
@@ -179,21 +180,29 @@ class DGPPO(Algorithm):
                 record=None, prof=None) -> Rollout:
         """InforMARL.collect (informarl.py:254-256): jit(vmap(rollout)) over the
         env keys == one batched rollout.  `b_key`: one key per environment."""
-        if graph0 is None:
-            graph0 = self._env.reset(b_key)
+        fresh = graph0 is None
+        if fresh:
+            graph0 = self._env.reset(b_key, defer_check=True)      # the feasibility flag is read back below
         b, T = graph0.nodes.shape[0], self._env.max_episode_steps
         if eps is None:
             eps = self._eps_from_key(b_key, (b, T, self.n_agents, self.action_dim))
-        return run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
-                                   self.init_rnn_state, record=record, n_chunks=self.rollout_chunks, prof=prof)
+        ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
+                                 self.init_rnn_state, record=record, n_chunks=self.rollout_chunks, prof=prof)
+        if fresh:
+            check_reset(self._env)                                  # after the rollout is enqueued
+        return ro
 
     def det_rollout_fn(self, params: dict, b_key, graph0: Optional[GraphsTuple] = None, record=None) -> Rollout:
         """DGPPO.det_rollout_fn (dgppo.py:108-117): test_rollout with algo.act."""
-        if graph0 is None:
-            graph0 = self._env.reset(b_key)
-        return run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
-                                   self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True,
-                                   n_chunks=self.rollout_chunks)
+        fresh = graph0 is None
+        if fresh:
+            graph0 = self._env.reset(b_key, defer_check=True)
+        ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
+                                 self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True,
+                                 n_chunks=self.rollout_chunks)
+        if fresh:
+            check_reset(self._env)
+        return ro
 
     @staticmethod
     def _record_arrays(rollout: Rollout):

@@ -84,7 +84,7 @@ def _as_seeds(key) -> Tuple[np.ndarray, bool]:
     return k.astype(np.uint64), False
 
 
-def _reset_kernel(env, seeds: np.ndarray, dev, obs_len=(0.0, 0.0), theta=(0.0, 0.0)):
+def _reset_kernel(env, seeds: np.ndarray, dev, obs_len=(0.0, 0.0), theta=(0.0, 0.0), defer_check=False):
     """K0: sample obstacles / agents / goals for len(seeds) environments on the device."""
     b, n, sd = len(seeds), env.num_agents, env.state_dim
     n_obs = int(env.params.get("n_obs", 0))
@@ -99,11 +99,26 @@ def _reset_kernel(env, seeds: np.ndarray, dev, obs_len=(0.0, 0.0), theta=(0.0, 0
     _lib.check(_lib.lib().dgppo_reset(stream_ptr(), C.byref(cfg), ptr(keys), float(obs_len[0]), float(obs_len[1]),
                                        float(theta[0]), float(theta[1]), ptr(agent), ptr(goal), ptr(obst),
                                        ptr(draws), b), "dgppo_reset")
+    env._reset_flags = draws
+    if not defer_check:
+        check_reset(env)
+    return agent, goal, obst
+
+
+def check_reset(env) -> None:
+    """Raise if the last device-side reset flagged an environment whose area cannot hold the agents
+    (K0 gives up after 16 restarts; the reference's sampler loops for ever: env/utils.py:229-232).
+    Reads one flag vector back: callers that want to keep the stream busy (algo.collect) reset with
+    the check deferred and call this after the rollout has been enqueued."""
+    draws = getattr(env, "_reset_flags", None)
+    if draws is None:
+        return
+    env._reset_flags = None
     if bool((draws < 0).any()):
+        n, n_obs = env.num_agents, int(env.params.get("n_obs", 0))
         raise RuntimeError(f"reset: area_size={env.area_size} cannot hold {n} agents + goals"
                            f"{' + ' + str(n_obs) + ' obstacles' if n_obs else ''} at the required spacing "
                            "(the reference's sampler does not terminate for this configuration)")
-    return agent, goal, obst
 
 
 def _batchify(*ts):
@@ -228,12 +243,13 @@ class LidarEnv(_KernelEnv):
             self._rays = dev_f32(tab, device)
         return self._rays
 
-    def reset(self, key) -> GraphsTuple:
+    def reset(self, key, defer_check: bool = False) -> GraphsTuple:
         """LidarEnv.reset (lidar_env/base.py:89-124): sampling on the device (K0), then LiDAR + graph."""
         dev = require_cuda()
         seeds, single = _as_seeds(key)
         assert self._params["n_obs"] >= 0
-        agent, goal, rec = _reset_kernel(self, seeds, dev, self._params["obs_len_range"], self._OBS_THETA)
+        agent, goal, rec = _reset_kernel(self, seeds, dev, self._params["obs_len_range"], self._OBS_THETA,
+                                         defer_check=defer_check)
         obstacles = Rectangle.from_record(rec, dev) if rec is not None else None
         env_state = LidarEnvState(agent, goal, obstacles)
         lidar = self.get_lidar_data(env_state.agent, obstacles)
@@ -402,11 +418,11 @@ class MPE(_KernelEnv):
     def node_dim(self) -> int:
         return 7
 
-    def reset(self, key) -> GraphsTuple:
+    def reset(self, key, defer_check: bool = False) -> GraphsTuple:
         """MPE.reset (mpe/base.py:81-127): sampling on the device (K0), then the graph."""
         dev = require_cuda()
         seeds, single = _as_seeds(key)
-        agent, goal, obs = _reset_kernel(self, seeds, dev)
+        agent, goal, obs = _reset_kernel(self, seeds, dev, defer_check=defer_check)
         env_state = MPEEnvState(agent, goal, obs)
         g = self.get_graph(env_state)
         if single:

@@ -99,3 +99,19 @@ def test_reset_infeasible_area_terminates_and_is_flagged():
     env = make_env("LidarSpread", num_agents=64, num_obs=64)
     with pytest.raises(RuntimeError, match="cannot hold"):
         env.reset(np.arange(4, dtype=np.uint64))
+
+
+def test_collect_raises_for_infeasible_area():
+    """algo.collect resets with the feasibility check deferred past the rollout launches; it must still raise."""
+    from dgppo_b200.algo import make_algo
+    from dgppo_b200.env import make_env
+    env = make_env("LidarSpread", num_agents=64, num_obs=64, max_step=2)
+    algo = make_algo("dgppo", env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
+                     action_dim=env.action_dim, n_agents=64, batch_size=4)
+    with pytest.raises(RuntimeError, match="cannot hold"):
+        algo.collect(algo.params, np.arange(4, dtype=np.uint64))
+    # and a feasible environment leaves no stale flag behind
+    env2 = make_env("LidarSpread", num_agents=3, num_obs=3, max_step=2)
+    algo2 = make_algo("dgppo", env=env2, node_dim=7, edge_dim=4, state_dim=4, action_dim=2, n_agents=3, batch_size=4)
+    ro = algo2.collect(algo2.params, np.arange(4, dtype=np.uint64))
+    assert ro.actions.shape == (4, 2, 3, 2)
