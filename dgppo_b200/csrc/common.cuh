@@ -36,6 +36,26 @@ struct GraphDims {
   int sd, nd, n_on, N, E, n_ag, n_ao, n, g;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may start while its
+// predecessor on the stream is still running; everything before pdl_wait() (weight staging into shared
+// memory) overlaps the predecessor's tail, pdl_wait() returns once the predecessor has completed and
+// its writes are visible.  pdl_launch_dependents() lets the NEXT kernel's blocks be scheduled early.
+// Both are no-ops for a kernel launched without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __host__ __device__ inline bool is_mpe(int kind) { return kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_TARGET; }
 __host__ __device__ inline bool is_lidar(int kind) { return !is_mpe(kind); }
 __host__ __device__ inline bool is_spread(int kind) { return kind == DGPPO_ENV_LIDAR_SPREAD || kind == DGPPO_ENV_MPE_SPREAD; }

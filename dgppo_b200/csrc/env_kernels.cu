@@ -347,6 +347,7 @@ build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
                    int* __restrict__ receivers, int* __restrict__ senders, int* __restrict__ node_type,
                    int* __restrict__ n_node, int* __restrict__ n_edge, int pitch, int b) {
   extern __shared__ float smem[];
+  pdl_launch_dependents();                       // the next policy forward may start staging its weights
   const int env = blockIdx.x;
   if (env >= b) return;
   constexpr int sd = SD, nd = SD + 3;
