@@ -137,11 +137,6 @@ __device__ __forceinline__ float gate_tanh(float x) {
 // i.e. below 1e-6 wherever exp(x) still matters; the weights that dominate the sum have x near 0.
 __device__ __forceinline__ float softmax_exp(float x) { return __expf(x); }
 
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -20,5 +20,6 @@ reference ships no tests or golden vectors.
 
 Arithmetic convention: fp32 everywhere, every add/mul/div/sqrt individually
 rounded (no FMA contraction) - the semantics NumPy gives and the semantics
-the CUDA env kernels are compiled to (``-fmad=false``).
+the CUDA env kernels spell out (``__fadd_rn`` / ``__fmul_rn`` / ``__fdiv_rn`` / ``__fsqrt_rn``,
+which nvcc never contracts into FMAs).
 """
