@@ -40,7 +40,7 @@ class DgppoNetLayout(C.Structure):
                                           "total")])
 
 
-ABI_VERSION = 2        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
+ABI_VERSION = 3        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
 
 _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 
@@ -73,6 +73,9 @@ SIGNATURES = {
     "dgppo_gnn_value": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
                                   _fp, _fp, _fp, _fp, C.c_int32,
                                   _fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32]),
+    "dgppo_vl_scan": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
+                                _fp, _fp, _fp, _fp, C.c_int32,
+                                _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32]),
     "dgppo_gae": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, _fp, _fp,
                             C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dgppo_cbf_advantage": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float,

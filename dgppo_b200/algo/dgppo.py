@@ -268,8 +268,9 @@ class DGPPO(Algorithm):
 
     def scan_Vl(self, rollout: Rollout, params: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """InforMARL.scan_Vl + final Vl (informarl.py:281-293, dgppo.py:204-216):
-        the centralised value is recurrent over T, so T+1 launches, each over
-        the b graphs of one slot.  -> Vl (b, T+1), carries (b, T+1, 64)."""
+        the centralised value is recurrent over T only through its GRU, so the
+        GNN layers of all slots run at once and the head runs T+1 times
+        (dgppo_vl_scan).  -> Vl (b, T+1), carries (b, T+1, 64)."""
         g = rollout.graph
         b, T = rollout.rewards.shape
         nodes, edges, recv, send = self._record_arrays(rollout)
@@ -278,15 +279,13 @@ class DGPPO(Algorithm):
         carry = torch.zeros((b, T + 2, RNN_DIM), dtype=torch.float32, device=dev)
         carry[:, 0] = self.init_Vl_rnn_state.reshape(RNN_DIM)
         Vl = torch.empty((b, T + 1), dtype=torch.float32, device=dev)
-        cfg, lib, pv = self._env.env_cfg(), _lib.lib(), self.packed("Vl", params)
-        es = 4
-        for t in range(T + 1):
-            _lib.check(lib.dgppo_gnn_value(
-                stream_ptr(), C.byref(cfg), C.byref(self.Vl_cfg), ptr(pv),
-                nodes.data_ptr() + t * d.n_nodes * d.node_dim * es, edges.data_ptr() + t * d.n_edges * 4 * es,
-                recv.data_ptr() + t * d.n_edges * 4, send.data_ptr() + t * d.n_edges * 4, T + 1,
-                carry.data_ptr() + t * RNN_DIM * es, carry.data_ptr() + (t + 1) * RNN_DIM * es, T + 2,
-                Vl.data_ptr() + t * es, T + 1, 1, b), "dgppo_gnn_value(Vl)")
+        cfg, pv = self._env.env_cfg(), self.packed("Vl", params)
+        # one launch of the GNN layers over all b * (T + 1) graphs (no recurrence there), then the
+        # GRU head slot by slot inside the library
+        _lib.check(_lib.lib().dgppo_vl_scan(
+            stream_ptr(), C.byref(cfg), C.byref(self.Vl_cfg), ptr(pv),
+            ptr(nodes), ptr(edges), ptr(recv), ptr(send), T + 1,
+            ptr(carry), T + 2, ptr(Vl), T + 1, T + 1, b), "dgppo_vl_scan")
         return Vl, carry[:, :T + 1]
 
     def gae(self, costs, neg_rewards, Vh, Vl) -> Tuple[torch.Tensor, torch.Tensor]:

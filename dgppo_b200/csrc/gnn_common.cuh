@@ -91,7 +91,9 @@ __device__ __forceinline__ void policy_tail(const GnnArgs& g, float m0, float m1
 // v2 launcher (gnn_v2.cu): returns DGPPO_V2_UNSUPPORTED when the shape does not
 // fit its shared-memory plan; the caller then uses the v1 fused kernel.
 #define DGPPO_V2_UNSUPPORTED (-100)
+// phase: 0 = GNN layers + head, 1 = GNN layers only (embeddings left in rnn_out), 2 = head only
+// (embeddings expected in rnn_out); 1 and 2 serve the Vl scan, whose GNN part has no recurrence.
 int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const float* params,
-                  const GnnArgs& g, int sms);
+                  const GnnArgs& g, int sms, int phase = 0);
 
 }  // namespace dgppo

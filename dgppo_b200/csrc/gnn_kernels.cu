@@ -479,7 +479,7 @@ static int fill_layout(const DgppoNetCfg* net, DgppoNetLayout* L) {
 }
 
 static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
-                      const float* params, GnnArgs g) {
+                      const float* params, GnnArgs g, int phase = 0) {
   DgppoNetLayout L;
   if (int rc = fill_layout(net, &L)) return rc;
   if (int rc = check_env_cfg(env)) return rc;
@@ -509,9 +509,10 @@ static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* n
   // v2 (weight-stationary pair of kernels) when the shape fits; v1 fused kernel otherwise
   const char* force_v1 = getenv("DGPPO_FORCE_V1");
   if (!(force_v1 && force_v1[0] == '1')) {
-    const int rc2 = launch_gnn_v2(stream, P, L, params, g, sms);
+    const int rc2 = launch_gnn_v2(stream, P, L, params, g, sms, phase);
     if (rc2 != DGPPO_V2_UNSUPPORTED) return rc2;
   }
+  if (phase != 0) return DGPPO_V2_UNSUPPORTED;      // the fused fallback kernel cannot be split
 
   const size_t x0_fl = (size_t)m_cap * X0S > (size_t)HID * RS ? (size_t)m_cap * X0S : (size_t)HID * RS;
   const size_t fl = x0_fl + (net->n_layers == 2 ? (size_t)m_cap * X1S : 0) +
@@ -573,4 +574,46 @@ extern "C" int dgppo_gnn_value(void* stream, const DgppoEnvCfg* env, const Dgppo
   g.eps = nullptr; g.eps_pitch = 1; g.action = nullptr; g.log_pi = nullptr; g.act_pitch = 1;
   g.value = value; g.out_pitch = out_pitch; g.n_graphs = b * n_slots;
   return launch_gnn(stream, env, net, params, g);
+}
+
+extern "C" int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                             const float* params, const float* nodes, const float* edges,
+                             const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                             float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
+                             int32_t n_slots, int32_t b) {
+  if (!net || net->kind != DGPPO_NET_VL) return DGPPO_EINVAL;
+  if (b < 0 || !params || !nodes || !edges || !receivers || !senders || !carry || !value) return DGPPO_EINVAL;
+  if (pitch < 1 || out_pitch < 1 || n_slots < 1 || n_slots > pitch || n_slots > out_pitch ||
+      carry_pitch < n_slots + 1) return DGPPO_EINVAL;
+  if (b == 0) return 0;
+  GnnArgs g{};
+  g.nodes = nodes; g.edges = edges; g.recv = receivers; g.send = senders; g.pitch = pitch;
+  g.eps = nullptr; g.eps_pitch = 1; g.action = nullptr; g.log_pi = nullptr; g.act_pitch = 1;
+  g.rnn_pitch = carry_pitch; g.out_pitch = out_pitch;
+  // phase 1: the GNN part of every slot has no recurrence: one launch over all b * n_slots graphs,
+  // embeddings parked in the carry rows they will be overwritten in (slot t -> carry slot t + 1)
+  g.n_slots = n_slots; g.n_graphs = b * n_slots;
+  g.rnn_in = carry; g.rnn_out = carry + HID; g.value = value;
+  int rc = launch_gnn(stream, env, net, params, g, 1);
+  if (rc == DGPPO_V2_UNSUPPORTED) {                   // shape outside the split kernels: slot by slot
+    for (int t = 0; t < n_slots; ++t) {
+      GnnArgs s = g;
+      s.nodes = nodes + (size_t)t * graph_dims(*env).N * graph_dims(*env).nd;
+      s.edges = edges + (size_t)t * graph_dims(*env).E * 4;
+      s.recv = receivers + (size_t)t * graph_dims(*env).E; s.send = senders + (size_t)t * graph_dims(*env).E;
+      s.n_slots = 1; s.n_graphs = b;
+      s.rnn_in = carry + (size_t)t * HID; s.rnn_out = carry + (size_t)(t + 1) * HID; s.value = value + t;
+      if ((rc = launch_gnn(stream, env, net, params, s, 0))) return rc;
+    }
+    return 0;
+  }
+  if (rc) return rc;
+  // phase 2: the recurrent head, slot by slot (carry t -> carry t + 1, value t)
+  for (int t = 0; t < n_slots; ++t) {
+    GnnArgs s = g;
+    s.n_slots = 1; s.n_graphs = b;
+    s.rnn_in = carry + (size_t)t * HID; s.rnn_out = carry + (size_t)(t + 1) * HID; s.value = value + t;
+    if ((rc = launch_gnn(stream, env, net, params, s, 2))) return rc;
+  }
+  return 0;
 }

@@ -1196,7 +1196,7 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
 
 
 int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const float* params,
-                  const GnnArgs& g_in, int sms) {
+                  const GnnArgs& g_in, int sms, int phase) {
   if (!g_in.rnn_out || g_in.rnn_out == g_in.rnn_in) return DGPPO_V2_UNSUPPORTED;
   GnnArgs g = g_in;
   const bool big = g.n > R2;
@@ -1236,8 +1236,10 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   const bool pdl = pdl_mode == 1 || pdl_mode == 2, pdl_h = pdl_mode == 1 || pdl_mode == 3;
   const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
   const int grid1 = n_tiles < 2 * sms ? n_tiles : 2 * sms;
-  cudaError_t err;
-  if (big) {
+  cudaError_t err = cudaSuccess;
+  if (phase == 2) {
+    // head only: the embeddings are already in rnn_out
+  } else if (big) {
     const int gridb = g.n_graphs < sms ? g.n_graphs : sms;
     if (P.n_layers == 2) {
       err = cudaFuncSetAttribute(gnn_layers_big_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
@@ -1259,6 +1261,7 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   }
   err = cudaGetLastError();
   if (err != cudaSuccess) return (int)err;
+  if (phase == 1) return 0;
   const int nr = (P.kind == DGPPO_NET_VL) ? 1 : g.n;
   const long total_rows = (long)g.n_graphs * nr;
   const long h_tiles = (total_rows + R - 1) / R;             // CTAs worth of 8-row warp tiles

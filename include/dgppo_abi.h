@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DGPPO_ABI_VERSION 2
+#define DGPPO_ABI_VERSION 3
 
 /* negative error codes (positive values are cudaError_t) */
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
@@ -258,6 +258,21 @@ int dgppo_gnn_value(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net
                     const int32_t* receivers, const int32_t* senders, int32_t pitch,
                     const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
                     float* value, int32_t out_pitch, int32_t n_slots, int32_t b);
+
+/* ---- Vl scan ---------------------------------------------------------------
+ * InforMARL.scan_Vl + the final Vl (informarl.py:281-293, dgppo.py:204-216): the
+ * centralised value over slots 0..n_slots-1 of every env, the GRU carry threaded
+ * through the slots.  Only the GRU is recurrent: the GNN layers of ALL b * n_slots
+ * graphs run as one launch, then the head / GRU / output runs slot by slot.
+ *   carry  (b, carry_pitch, 64), carry_pitch >= n_slots + 1: slot 0 = initial carry
+ *          in, slot t + 1 = carry after slot t out (slots 1.. are scratch in between)
+ *   value  (b, out_pitch) out, slot t at [e * out_pitch + t]                        */
+int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                  const float* params,
+                  const float* nodes, const float* edges,
+                  const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                  float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
+                  int32_t n_slots, int32_t b);
 
 /* ---- K5: GAE ---------------------------------------------------------------
  * compute_dec_ocp_gae (algo/utils.py:11-79; callers dgppo.py:232-237,268-273).

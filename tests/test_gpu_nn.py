@@ -138,3 +138,40 @@ def test_head_kernel_variants(head, monkeypatch, kernel_generation):
     _close(h, h32, h64, f"rnn {head}")
     _close(a, a32, a64, f"action {head}")
     _close(lp, lp32, lp64, f"log_pi {head}")
+
+
+@pytest.mark.parametrize("name", ["C1", "C3", "mpe20"])
+def test_vl_scan_matches_slot_by_slot_and_oracle(name):
+    """dgppo_vl_scan (GNN layers of all slots in one launch, GRU head slot by slot) against the oracle's
+    recurrent replay (informarl.py:281-293) and against dgppo_gnn_value called slot by slot (bit-identical:
+    the same kernels see the same rows).  Runs on the split v2 kernels and on the v1 fallback loop."""
+    import ctypes as C
+    import torch
+    from tests.util import dev, p, stream
+    cfg = CONFIGS[name]
+    b, S = 7, 5
+    graphs = [_graph(cfg, b, 100 + t) for t in range(S)]
+    tree = P.init_value_params(cfg.node_dim, 4, 1, 2, seed=6, jitter=0.1)
+    nc = P.net_cfg(_lib.NET_VL, cfg.node_dim, 4, 2, 1)
+    packed = P.pack_params(tree, nc)
+    h0 = (np.random.default_rng(3).standard_normal(64) * 0.3).astype(F)
+    stack = {k: np.stack([g[k] for g in graphs], axis=1) for k in ("nodes", "edges", "receivers", "senders")}
+    nodes, edges = dev(stack["nodes"]), dev(stack["edges"])
+    recv, send = dev(stack["receivers"], torch.int32), dev(stack["senders"], torch.int32)
+    carry = torch.zeros((b, S + 1, 64), device="cuda")
+    carry[:, 0] = dev(h0)
+    val = torch.empty((b, S), device="cuda")
+    pk, cc = dev(packed), util.c_cfg(cfg)
+    _lib.check(_lib.lib().dgppo_vl_scan(stream(), C.byref(cc), C.byref(nc), p(pk), p(nodes), p(edges), p(recv), p(send),
+                                         S, p(carry), S + 1, p(val), S, S, b), "dgppo_vl_scan")
+    torch.cuda.synchronize()
+    val_h, carry_h = val.cpu().numpy(), carry.cpu().numpy()
+    h32 = np.broadcast_to(h0, (b, 64)).copy()
+    h_slot = h32.copy()
+    for t in range(S):
+        v32, h32 = nn_np.vl_forward(tree, graphs[t], h32, cfg.n, 2, np.float32)
+        np.testing.assert_allclose(val_h[:, t], v32, rtol=2e-5, atol=2e-5, err_msg=f"Vl slot {t}")
+        np.testing.assert_allclose(carry_h[:, t + 1], h32, rtol=2e-5, atol=2e-5, err_msg=f"carry slot {t}")
+        v_slot, h_slot = util.k_value(cfg, nc, packed, graphs[t], h_slot)
+        util.assert_bits_equal(val_h[:, t], v_slot.astype(F), f"scan vs slot-by-slot value {t}")
+        util.assert_bits_equal(carry_h[:, t + 1], h_slot, f"scan vs slot-by-slot carry {t}")
