@@ -373,9 +373,9 @@ def run_gpu(args):
             "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel_wide", "bound": "hbm",
                          "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                          # dram__bytes_read + dram__bytes_write per launch pair from the committed ncu --set full
-                         # capture (C3, 4096 envs): gnn_layers 27.62 MB + head 17.54 MB read, 0.01 MB written
-                         "traffic": 45.18e6 if (args.workload == "C3" and b == 4096) else None,
-                         "traffic_source": "profiles/r1_policy_v4.ncu.txt",
+                         # capture (C3, 4096 envs): gnn_layers 27.63 MB + head 17.51 MB read, 0.03 MB written
+                         "traffic": 45.17e6 if (args.workload == "C3" and b == 4096) else None,
+                         "traffic_source": "profiles/r1_all_v6.ncu.txt",
                          "algorithmic_bytes_per_launch": pol_bytes * b,
                          "peak_source": which,
                          "note": "FP32-FFMA bound kernel reported against HBM as BASELINE's metric asks; "
