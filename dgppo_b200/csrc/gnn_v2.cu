@@ -1059,10 +1059,19 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
   const long n_wtiles = (total_rows + WR3 - 1) / WR3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = warp * WR3;
-  auto row_off = [&](long row) {
-    const long gi = row / nr; const int i = (int)(row - gi * nr);
-    const long env = gi / g.n_slots; const int slot = (int)(gi - env * g.n_slots);
-    return (((size_t)env * g.rnn_pitch + slot) * nr + i) * HID;
+  // row -> (env, slot, agent): 32-bit divisions when the row count allows, and once per row (lane i decodes
+  // the warp tile's row i; the others get the offset by shuffle) - the 64-bit form cost 10 % of the kernel
+  const bool small_rows = total_rows < 0x7fffffffL;
+  auto decode = [&](long row, int& env, int& slot, int& i) {
+    if (small_rows) {
+      const unsigned r = (unsigned)row, gi = r / (unsigned)nr;
+      i = (int)(r - gi * (unsigned)nr);
+      const unsigned e = (g.n_slots == 1) ? gi : gi / (unsigned)g.n_slots;
+      env = (int)e; slot = (int)(gi - e * (unsigned)g.n_slots);
+    } else {
+      const long gi = row / nr; i = (int)(row - gi * nr);
+      const long e = gi / g.n_slots; env = (int)e; slot = (int)(gi - e * g.n_slots);
+    }
   };
 
   // warp tiles are dealt round-robin over the CTAs (tile wt -> CTA wt % grid), so a partial last round
@@ -1071,12 +1080,18 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
     const long row0 = wt * WR3;
     const int rows = (int)min((long)WR3, total_rows - row0);
     __syncwarp();
+    int my_env = 0, my_slot = 0, my_i = 0;
+    unsigned long long my_off = 0;
+    if (lane < rows) {
+      decode(row0 + lane, my_env, my_slot, my_i);
+      my_off = (((size_t)my_env * g.rnn_pitch + my_slot) * nr + my_i) * HID;
+    }
     // embeddings (scratch rows in rnn_out) -> b0 (transposed, async); previous carry -> registers
     float hreg[WR3][2];
 #pragma unroll
     for (int i = 0; i < WR3; ++i) {
       if (i < rows) {
-        const size_t off = row_off(row0 + i);
+        const size_t off = __shfl_sync(0xffffffffu, my_off, i);
         cp_async4(b0 + lane * R3S + r0 + i, g.rnn_out + off + lane);
         cp_async4(b0 + (lane + 32) * R3S + r0 + i, g.rnn_out + off + lane + 32);
         const float2 hv = __ldg(reinterpret_cast<const float2*>(g.rnn_in + off) + lane);   // units 2 lane, 2 lane + 1
@@ -1168,7 +1183,7 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
 #pragma unroll
     for (int i = 0; i < WR3; ++i)                                   // new carry, one float2 per lane (coalesced)
       if (i < rows)
-        reinterpret_cast<float2*>(g.rnn_out + row_off(row0 + i))[lane] = make_float2(hn[i][0], hn[i][1]);
+        reinterpret_cast<float2*>(g.rnn_out + __shfl_sync(0xffffffffu, my_off, i))[lane] = make_float2(hn[i][0], hn[i][1]);
     __syncwarp();
     const float* feat = b0;                                         // ScaleHid is folded into out_w at pack time
     {   // out: [64] -> 4 columns; lane = (row, column)
@@ -1181,11 +1196,9 @@ head_kernel_wide(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ pa
     __syncwarp();
     if (lane < rows) {
       const int r = r0 + lane;
-      const long row = row0 + lane;
-      const long gi = row / nr; const int i = (int)(row - gi * nr);
-      const long env = gi / g.n_slots; const int slot = (int)(gi - env * g.n_slots);
+      const int env = my_env, slot = my_slot, i = my_i;
       if (policy) {
-        policy_tail(g, o4[r], o4[R3S + r], o4[2 * R3S + r], o4[3 * R3S + r], (int)env, slot, i, n);
+        policy_tail(g, o4[r], o4[R3S + r], o4[2 * R3S + r], o4[3 * R3S + r], env, slot, i, n);
       } else {
         float* vo = g.value + ((((size_t)env * g.out_pitch + slot) * nr + i) * net.n_out);
         for (int c = 0; c < net.n_out; ++c) vo[c] = o4[c * R3S + r];
