@@ -295,6 +295,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
   auto wptr = [&](const float* p) { return ws + ((p - params) - pl.w_off); };
 
   const int n = g.n, N = g.N, nd = g.nd, G = g.G, deg = pl.deg, degp = pl.degp;
+  const int dshift = (degp == 32) ? 5 : 6;
   const int nodes_per = N - 1, pad = N - 1;
   const int n_tiles = (g.n_graphs + G - 1) / G;
   const int nr_out = (net.kind == DGPPO_NET_VL) ? 1 : n;
@@ -336,7 +337,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       }
     }
     for (int idx = threadIdx.x; idx < R2 * degp; idx += nth) {
-      const int r = idx / degp, t = idx - r * degp;      // degp is 32 or 64
+      const int r = idx >> dshift, t = idx & (degp - 1);  // degp is 32 or 64
       int s = -1;
       const int gl = tab[r];
       if (gl >= 0 && t < deg) {
@@ -411,6 +412,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       //      concurrently and leave partial sums in smem (scr / qt are dead by now):
       //      upper warps: k in [kh, H*INA) of z Wagg; lower warps: k in [0, kh) + x Wu.
       const int KZ = H * INA, kh = KZ / 2, hw = nwarps / 2;
+      const int qshift = (D == 32) ? 3 : 4;
       float* part_hi = qt;                                            // [R2][64]
       float* part_lo = scr;                                           // [R2][64]
       auto store_part = [&](float* dstp) {
@@ -461,7 +463,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       __syncthreads();
       float* ob = x0;                                                 // Vl only: [64][RS2] (x0 is dead by then)
       for (int idx = threadIdx.x; idx < R2 * (D / 4); idx += nth) {   // combine + bias + relu
-        const int r = idx / (D / 4), c0 = (idx - r * (D / 4)) * 4;
+        const int r = idx >> qshift, c0 = (idx & ((D >> 2) - 1)) * 4;   // D / 4 is 8 or 16
         const float4 lo = *reinterpret_cast<const float4*>(part_lo + r * 64 + c0);
         const float4 hi = *reinterpret_cast<const float4*>(part_hi + r * 64 + c0);
         const float4 v = make_float4(fmaxf(lo.x + hi.x + bu[c0], 0.f), fmaxf(lo.y + hi.y + bu[c0 + 1], 0.f),
@@ -749,6 +751,7 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
         }
         __syncthreads();
         const int KZ = H * INA, kh = KZ / 2, hw = nwarps / 2;
+        const int qshift = (D == 32) ? 3 : 4;
         float* part_hi = qt;                                            // [R2][64]
         float* part_lo = scr;                                           // [R2][64]
         auto store_part = [&](float* dstp) {
@@ -765,7 +768,7 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
         __syncthreads();
         float* ob = z;                                                  // Vl only: [64][RS2]
         for (int idx = threadIdx.x; idx < R2 * (D / 4); idx += nth) {   // combine + bias + relu
-          const int r = idx / (D / 4), c0 = (idx - r * (D / 4)) * 4;
+          const int r = idx >> qshift, c0 = (idx & ((D >> 2) - 1)) * 4;   // D / 4 is 8 or 16
           const float4 lo = *reinterpret_cast<const float4*>(part_lo + r * 64 + c0);
           const float4 hi = *reinterpret_cast<const float4*>(part_hi + r * 64 + c0);
           const float4 v = make_float4(fmaxf(lo.x + hi.x + bu[c0], 0.f), fmaxf(lo.y + hi.y + bu[c0 + 1], 0.f),
