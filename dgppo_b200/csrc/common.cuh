@@ -56,9 +56,13 @@ inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-__host__ __device__ inline bool is_mpe(int kind) { return kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_TARGET; }
+__host__ __device__ inline bool is_mpe(int kind) {
+  return kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_TARGET || kind == DGPPO_ENV_MPE_CORRIDOR;
+}
 __host__ __device__ inline bool is_lidar(int kind) { return !is_mpe(kind); }
-__host__ __device__ inline bool is_spread(int kind) { return kind == DGPPO_ENV_LIDAR_SPREAD || kind == DGPPO_ENV_MPE_SPREAD; }
+__host__ __device__ inline bool is_spread(int kind) {
+  return kind == DGPPO_ENV_LIDAR_SPREAD || kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_CORRIDOR;
+}
 __host__ __device__ inline bool is_bicycle(int kind) { return kind == DGPPO_ENV_LIDAR_BICYCLE_TARGET; }
 
 __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
@@ -78,7 +82,8 @@ __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
 
 inline int check_env_cfg(const DgppoEnvCfg* c) {
   if (!c) return DGPPO_EINVAL;
-  if (c->kind < 0 || c->kind > 4) return DGPPO_ENOTSUP;
+  if (c->kind < 0 || c->kind > 5) return DGPPO_ENOTSUP;
+  if (c->kind == DGPPO_ENV_MPE_CORRIDOR && c->n_obs != 2) return DGPPO_EINVAL;       // mpe_corridor.py:33-35
   if (c->n_agents < 1 || c->n_obs < 0) return DGPPO_EINVAL;
   if (is_lidar(c->kind) && c->n_obs > 0) {
     if (c->n_rays < 1 || c->n_rays > 1024) return DGPPO_ENOTSUP;

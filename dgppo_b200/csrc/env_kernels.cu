@@ -11,7 +11,7 @@ namespace dgppo {
 
 struct EnvConsts {
   int kind, n, n_obs, n_rays, top_k;
-  float dt, R, R_diag, R_obs, car2, car, car_obs, d2g;
+  float dt, R, R_diag, R_obs, R_mpe_obs, car2, car, car_obs, d2g;
   float lo[5], hi[5];
 };
 
@@ -22,6 +22,8 @@ static EnvConsts make_consts(const DgppoEnvCfg& c) {
   k.R = (float)c.comm_radius;
   k.R_diag = (float)(c.comm_radius + 1.0);          // lidar_spread.py:64
   k.R_obs = (float)(c.comm_radius - 1e-1);          // lidar_spread.py:87
+  // MPE agent-obstacle edges: within comm_radius (mpe_spread.py:73-75); always on in the corridor (x100: mpe_corridor.py:93)
+  k.R_mpe_obs = (float)(c.kind == DGPPO_ENV_MPE_CORRIDOR ? c.comm_radius * 100 : c.comm_radius);
   k.car2 = (float)(c.car_radius * 2.0);             // lidar_env/base.py:188
   k.car = (float)c.car_radius;                      // lidar_env/base.py:197
   k.car_obs = (float)(c.car_radius + c.obs_radius); // mpe/base.py:181
@@ -32,7 +34,8 @@ static EnvConsts make_consts(const DgppoEnvCfg& c) {
     for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
   } else {
     const float v = is_mpe(c.kind) ? 1.0f : 0.5f;   // mpe/base.py:243-246 | lidar_env/base.py:273-276
-    const float lo[5] = {0.f, 0.f, -v, -v, 0.f}, hi[5] = {A, A, v, v, 0.f};
+    const float Ay = (c.kind == DGPPO_ENV_MPE_CORRIDOR) ? (float)(c.area_size * 2) : A;   // mpe_corridor.py:64-67
+    const float lo[5] = {0.f, 0.f, -v, -v, 0.f}, hi[5] = {A, Ay, v, v, 0.f};
     for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
   }
   return k;
@@ -457,7 +460,7 @@ build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
       } else {                                               // mpe_spread.py:70-79
         const float* a = sa + i * sd; const float* c = so + q * 4;
         f = make_float4(fsub(a[0], c[0]), fsub(a[1], c[1]), fsub(a[2], c[2]), fsub(a[3], c[3]));
-        m = norm2(f.x, f.y) < k.R; rcv = i; snd = n + g + q;
+        m = norm2(f.x, f.y) < k.R_mpe_obs; rcv = i; snd = n + g + q;
       }
     }
     oe_[e] = f;

@@ -18,7 +18,8 @@ namespace dgppo {
 
 struct ResetConsts {
   int kind, n, n_obs;
-  float area, min_dist, car, obs_r, len_lo, len_hi, th_lo, th_hi;
+  float area, area_y, goal_shift_y, min_dist, car, obs_r, len_lo, len_hi, th_lo, th_hi;
+  float fixed_obs[4];          // MPECorridor: the two obstacle centres (mpe_corridor.py:53-54)
 };
 
 __host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
@@ -113,22 +114,22 @@ reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* 
   while (agent_id < n) {
     // agent candidate: redraw while it collides / lies in an obstacle, at most max_iter times
     float2 u = rng.next2();
-    float cx = fmul(u.x, k.area), cy = fmul(u.y, k.area);
+    float cx = fmul(u.x, k.area), cy = fmul(u.y, k.area_y);          // max_side = [side_length, side_length_y]
     int it_a = 0;
     while (it_a < RESET_MAX_ITER &&
            (collides(cx, cy, st, n, k.min_dist, lane) || (n_rect > 0 && inside_any(cx, cy, recp, n_rect, half, lane)))) {
-      ++it_a; u = rng.next2(); cx = fmul(u.x, k.area); cy = fmul(u.y, k.area);
+      ++it_a; u = rng.next2(); cx = fmul(u.x, k.area); cy = fmul(u.y, k.area_y);
     }
     __syncwarp();
     if (lane == 0) { st[2 * agent_id] = cx; st[2 * agent_id + 1] = cy; }
     __syncwarp();
     u = rng.next2();
-    float gx = fmul(u.x, k.area), gy = fmul(u.y, k.area);
+    float gx = fmul(u.x, k.area), gy = fmul(u.y, k.area_y);
     int it_g = 0;
     while (it_g < RESET_MAX_ITER &&
            (collides(gx, gy, gl, n, k.min_dist, lane) || (n_rect > 0 && inside_any(gx, gy, recp, n_rect, half, lane)) ||
             gx < 0.f || gy < 0.f || gx > k.area || gy > k.area)) {
-      ++it_g; u = rng.next2(); gx = fmul(u.x, k.area); gy = fmul(u.y, k.area);
+      ++it_g; u = rng.next2(); gx = fmul(u.x, k.area); gy = fmul(u.y, k.area_y);
     }
     __syncwarp();
     if (lane == 0) { gl[2 * agent_id] = gx; gl[2 * agent_id + 1] = gy; }
@@ -144,7 +145,15 @@ reset_kernel(ResetConsts k, const unsigned long long* __restrict__ keys, float* 
 
   // ---- MPE obstacles (mpe/base.py:93-118): first candidate in [0, area]^2, redraws in [3r, area-3r]^2
   float* oo = obst + (size_t)env * k.n_obs * (lid ? DGPPO_OBS_STRIDE : 4);
-  if (!lid) {
+  if (k.kind == DGPPO_ENV_MPE_CORRIDOR) {
+    // goals move up by the corridor offset (mpe_corridor.py:50); the two obstacles are fixed (:53-54)
+    for (int j = lane; j < n; j += 32) gl[2 * j + 1] = fadd(gl[2 * j + 1], k.goal_shift_y);
+    if (lane < 2) {
+      oo[4 * lane] = k.fixed_obs[2 * lane]; oo[4 * lane + 1] = k.fixed_obs[2 * lane + 1];
+      oo[4 * lane + 2] = 0.f; oo[4 * lane + 3] = 0.f;
+    }
+    __syncwarp();
+  } else if (!lid) {
     const float lo = fmul(k.car, 3.f), hi = fsub(k.area, fmul(k.car, 3.f));
     for (int o = 0; o < k.n_obs; ++o) {
       float2 u = rng.next2();
@@ -193,6 +202,15 @@ extern "C" int dgppo_reset(void* stream, const DgppoEnvCfg* cfg, const uint64_t*
   ResetConsts k;
   k.kind = cfg->kind; k.n = cfg->n_agents; k.n_obs = cfg->n_obs;
   k.area = (float)cfg->area_size;
+  k.area_y = k.area; k.goal_shift_y = 0.f;
+  k.fixed_obs[0] = k.fixed_obs[1] = k.fixed_obs[2] = k.fixed_obs[3] = 0.f;
+  if (cfg->kind == DGPPO_ENV_MPE_CORRIDOR) {                 // mpe_corridor.py:39-54, Python doubles rounded once
+    const double A = cfg->area_size, ro = cfg->obs_radius, rc = cfg->car_radius;
+    k.area_y = (float)((A - ro * 2) / 2 - 1.5 * rc);
+    k.goal_shift_y = (float)(A - (A - ro * 2) / 2 + 1.5 * rc);
+    k.fixed_obs[0] = (float)ro; k.fixed_obs[1] = (float)(A / 2);
+    k.fixed_obs[2] = (float)(A - ro); k.fixed_obs[3] = (float)(A / 2);
+  }
   k.min_dist = (float)((is_lidar(cfg->kind) ? 2.2 : 2.0) * cfg->car_radius);   // lidar_env/base.py:111 | mpe/base.py:88
   k.car = (float)cfg->car_radius; k.obs_r = (float)cfg->obs_radius;
   k.len_lo = (float)obs_len_lo; k.len_hi = (float)obs_len_hi; k.th_lo = (float)theta_lo; k.th_hi = (float)theta_hi;

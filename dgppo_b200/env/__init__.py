@@ -1,17 +1,18 @@
 """Environment registry and factory (dgppo/env/__init__.py:9-53).
 
 The environments on BASELINE.json's configs are registered plus
-MPETarget, the first of the "other env families through the same kernels" row
-(SURVEY.md 8f.4); the remaining MPE / Lidar tasks and VMAS are outside this path.
+MPETarget and MPECorridor, the first of the "other env families through the same
+kernels" row; the remaining MPE / Lidar tasks and VMAS are outside this path.
 """
 from typing import Optional
 
 from .base import MultiAgentEnv, StepResult
 from .envs import (LidarBicycleTarget, LidarEnv, LidarEnvState, LidarSpread, LidarTarget, MPE,
-                   MPEEnvState, MPESpread, MPETarget, Rectangle)
+                   MPECorridor, MPEEnvState, MPESpread, MPETarget, Rectangle)
 
 ENV = {
     "MPETarget": MPETarget,
+    "MPECorridor": MPECorridor,
     "MPESpread": MPESpread,
     "LidarSpread": LidarSpread,
     "LidarTarget": LidarTarget,

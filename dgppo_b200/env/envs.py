@@ -506,3 +506,25 @@ class MPETarget(MPE):
     PARAMS = {"car_radius": 0.05, "comm_radius": 0.5, "n_obs": 3, "obs_radius": 0.05,
               "default_area_size": 1.5, "dist2goal": 0.01}
     KIND = 4
+
+
+class MPECorridor(MPE):
+    """dgppo/env/mpe/mpe_corridor.py: MPESpread with two fixed obstacles that leave a corridor of
+    `corridor_width` between them, agents sampled below it and goals above it, the y range doubled and
+    the agent-obstacle edges always on.  Same kernels, env kind 5."""
+    PARAMS = {"car_radius": 0.05, "comm_radius": 0.5, "default_area_size": 1.0, "dist2goal": 0.01,
+              "n_obs": 2, "corridor_width": 0.2}
+    KIND = 5
+
+    def __init__(self, num_agents, area_size=None, max_step=128, dt=0.03, params=None):
+        params = dict(type(self).PARAMS if params is None else params)
+        super().__init__(num_agents, area_size, max_step, dt, params)
+        if self._params["n_obs"] != 2:                                   # mpe_corridor.py:33-35
+            self._params["n_obs"] = 2
+            print("WARNING: n_obs is set to 2 for MPECorridor.")
+        # solve for the radius of the obstacles (mpe_corridor.py:36-37)
+        self._params["obs_radius"] = (self.area_size - self._params["corridor_width"]) / 4
+
+    def state_lim(self, state=None):
+        A = self.area_size
+        return torch.tensor([0., 0., -1., -1.]), torch.tensor([A, A * 2, 1., 1.])

@@ -41,12 +41,13 @@ extern "C" {
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
 #define DGPPO_ENOTSUP  (-2)   /* configuration outside what the kernels cover */
 
-/* env kinds (dgppo/env/__init__.py:9-23): the ones on BASELINE.json configs + MPETarget */
+/* env kinds (dgppo/env/__init__.py:9-23): the ones on BASELINE.json configs + MPETarget, MPECorridor */
 #define DGPPO_ENV_LIDAR_SPREAD          0  /* lidar_env/lidar_spread.py          */
 #define DGPPO_ENV_LIDAR_TARGET          1  /* lidar_env/lidar_target.py          */
 #define DGPPO_ENV_LIDAR_BICYCLE_TARGET  2  /* lidar_env/lidar_bicycle_target.py  */
 #define DGPPO_ENV_MPE_SPREAD            3  /* mpe/mpe_spread.py                  */
 #define DGPPO_ENV_MPE_TARGET            4  /* mpe/mpe_target.py (same kernels, paired goals) */
+#define DGPPO_ENV_MPE_CORRIDOR          5  /* mpe/mpe_corridor.py: MPESpread + 2 fixed obstacles, y <= 2 area, obstacle edges always on */
 
 /* Static environment description: the PARAMS dicts (lidar_spread.py:13-22,
  * mpe_spread.py:12-19) plus dt / num_agents (env/__init__.py:47-53). */

@@ -24,6 +24,7 @@ LIDAR_TARGET = 1          # dgppo/env/lidar_env/lidar_target.py
 LIDAR_BICYCLE_TARGET = 2  # dgppo/env/lidar_env/lidar_bicycle_target.py
 MPE_SPREAD = 3            # dgppo/env/mpe/mpe_spread.py
 MPE_TARGET = 4            # dgppo/env/mpe/mpe_target.py
+MPE_CORRIDOR = 5          # dgppo/env/mpe/mpe_corridor.py
 
 KIND_BY_NAME = {
     "LidarSpread": LIDAR_SPREAD,
@@ -31,6 +32,7 @@ KIND_BY_NAME = {
     "LidarBicycleTarget": LIDAR_BICYCLE_TARGET,
     "MPESpread": MPE_SPREAD,
     "MPETarget": MPE_TARGET,
+    "MPECorridor": MPE_CORRIDOR,
 }
 
 
@@ -53,7 +55,7 @@ class EnvCfg:
 
     @property
     def is_lidar(self) -> bool:
-        return self.kind not in (MPE_SPREAD, MPE_TARGET)
+        return self.kind not in (MPE_SPREAD, MPE_TARGET, MPE_CORRIDOR)
 
     @property
     def is_bicycle(self) -> bool:
@@ -89,7 +91,7 @@ class EnvCfg:
 
     @property
     def n_ag(self) -> int:               # goal senders per agent
-        return self.n_goal if self.kind in (LIDAR_SPREAD, MPE_SPREAD) else 1
+        return self.n_goal if self.kind in (LIDAR_SPREAD, MPE_SPREAD, MPE_CORRIDOR) else 1
 
     @property
     def n_ao(self) -> int:               # obstacle senders per agent
@@ -238,6 +240,8 @@ def state_lim(cfg: EnvCfg) -> Tuple[np.ndarray, np.ndarray]:
     A = cfg.area
     if cfg.is_bicycle:
         return np.array([0, 0, -1, -1, -0.5], F), np.array([A, A, 1, 1, 0.5], F)
+    if cfg.kind == MPE_CORRIDOR:                       # mpe_corridor.py:64-67
+        return np.array([0, 0, -1, -1], F), np.array([A, A * 2, 1, 1], F)
     if not cfg.is_lidar:
         return np.array([0, 0, -1, -1], F), np.array([A, A, 1, 1], F)
     return np.array([0, 0, -0.5, -0.5], F), np.array([A, A, 0.5, 0.5], F)
@@ -304,7 +308,7 @@ def get_reward(cfg: EnvCfg, agent: np.ndarray, goal: np.ndarray, action: np.ndar
     (lidar_env/base.py:160,170).  -> (b,)"""
     ax, ay = agent[..., 0], agent[..., 1]
     gx, gy = goal[..., 0], goal[..., 1]
-    if cfg.kind in (LIDAR_SPREAD, MPE_SPREAD):
+    if cfg.kind in (LIDAR_SPREAD, MPE_SPREAD, MPE_CORRIDOR):
         d = norm2((gx[:, :, None] - ax[:, None, :]).astype(F), (gy[:, :, None] - ay[:, None, :]).astype(F))
         dist2goal = d.min(axis=2)
     else:
@@ -419,7 +423,8 @@ def get_graph(cfg: EnvCfg, agent: np.ndarray, goal: np.ndarray,
             ao = (agent[:, :, None, :] - obs_nodes[:, None, :, :]).astype(F)
             d = norm2((px[:, :, None] - obs_nodes[:, None, :, 0]).astype(F),
                       (py[:, :, None] - obs_nodes[:, None, :, 1]).astype(F))
-            active = d < R
+            # within comm_radius (mpe_spread.py:73-75); always on in the corridor (x100: mpe_corridor.py:93)
+            active = d < (F(cfg.comm_radius * 100) if cfg.kind == MPE_CORRIDOR else R)
             edges[:, off:off + n * o] = ao.reshape(b, n * o, 4)
             sid = n + g + np.arange(o, dtype=np.int32)
             recv[:, off:off + n * o] = np.where(active, ids[None, :, None], pad).reshape(b, n * o)

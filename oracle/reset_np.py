@@ -72,24 +72,28 @@ def reset_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3), theta_range=N
     min_dist = F((2.2 if lid else 2.0) * cfg.car_radius)
     half = F(min_dist / F(2))
     st, gl = np.zeros((n, 2), F), np.zeros((n, 2), F)
+    corridor = cfg.kind == env_np.MPE_CORRIDOR
+    Ay = A
+    if corridor:     # mpe_corridor.py:39-50: side_length_y of the sampler, Python doubles rounded once
+        Ay = F((cfg.area - cfg.obs_radius * 2) / 2 - 1.5 * cfg.car_radius)
     agent_id = restarts = 0
     while agent_id < n:
         u = rng.next2()
-        c = (F(u[0] * A), F(u[1] * A))
+        c = (F(u[0] * A), F(u[1] * Ay))
         it_a = 0
         while it_a < MAX_ITER and (_collides(c, st, min_dist) or _inside_any(c, rec, half)):
             it_a += 1
             u = rng.next2()
-            c = (F(u[0] * A), F(u[1] * A))
+            c = (F(u[0] * A), F(u[1] * Ay))
         st[agent_id] = c
         u = rng.next2()
-        g = (F(u[0] * A), F(u[1] * A))
+        g = (F(u[0] * A), F(u[1] * Ay))
         it_g = 0
         while it_g < MAX_ITER and (_collides(g, gl, min_dist) or _inside_any(g, rec, half)
                                    or g[0] < 0 or g[1] < 0 or g[0] > A or g[1] > A):
             it_g += 1
             u = rng.next2()
-            g = (F(u[0] * A), F(u[1] * A))
+            g = (F(u[0] * A), F(u[1] * Ay))
         gl[agent_id] = g
         agent_id += 1
         if it_a >= MAX_ITER or it_g >= MAX_ITER:
@@ -100,7 +104,12 @@ def reset_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3), theta_range=N
             st[:] = 0
             gl[:] = 0
     obst = rec
-    if not lid and cfg.n_obs > 0:
+    if corridor:     # goals shifted past the corridor, two fixed obstacles (mpe_corridor.py:50-54)
+        gl[:, 1] = (gl[:, 1] + F(cfg.area - (cfg.area - cfg.obs_radius * 2) / 2 + 1.5 * cfg.car_radius)).astype(F)
+        obst = np.zeros((2, 4), F)
+        obst[0, :2] = (F(cfg.obs_radius), F(cfg.area / 2))
+        obst[1, :2] = (F(cfg.area - cfg.obs_radius), F(cfg.area / 2))
+    elif not lid and cfg.n_obs > 0:
         obst = np.zeros((cfg.n_obs, 4), F)
         car, obr = F(cfg.car_radius), F(cfg.obs_radius)
         lo, hi = F(car * F(3)), F(A - F(car * F(3)))

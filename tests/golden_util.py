@@ -17,6 +17,7 @@ CASES = {
     "MPESpread_n8_obs3": env_np.EnvCfg(env_np.MPE_SPREAD, n=8, n_obs=3),
     "LidarSpread_n4_obs0": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
     "MPETarget_n6_obs3": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
+    "MPECorridor_n5_obs2": env_np.EnvCfg(env_np.MPE_CORRIDOR, n=5, n_obs=2, area=1.0, obs_radius=0.2),
 }
 
 

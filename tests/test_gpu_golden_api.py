@@ -70,11 +70,12 @@ def _np_obstacles(rect):
 
 
 @pytest.mark.parametrize("env_id,n,obs", [("LidarSpread", 3, 3), ("LidarTarget", 4, 2), ("LidarBicycleTarget", 4, 3),
-                                          ("MPESpread", 5, 3), ("MPETarget", 6, 3)])
+                                          ("MPESpread", 5, 3), ("MPETarget", 6, 3), ("MPECorridor", 5, 2)])
 def test_env_api_reset_step(env_id, n, obs):
     from dgppo_b200.env import make_env
     env = make_env(env_id, num_agents=n, num_obs=obs)
-    cfg = env_np.EnvCfg(env_np.KIND_BY_NAME[env_id], n=n, n_obs=obs)
+    cfg = env_np.EnvCfg(env_np.KIND_BY_NAME[env_id], n=n, n_obs=obs, area=env.area_size,
+                        obs_radius=env.params.get("obs_radius", 0.05))
     g = env.reset(np.arange(10))
     assert g.nodes.shape == (10, cfg.n_nodes, cfg.node_dim) and g.receivers.dtype == torch.int32
     # reset honours the reference's rejection rules (env/utils.py:169-204)

@@ -19,6 +19,7 @@ CASES = {
     "LidarBicycleTarget": env_np.EnvCfg(env_np.LIDAR_BICYCLE_TARGET, n=4, n_obs=3),
     "MPESpread": env_np.EnvCfg(env_np.MPE_SPREAD, n=8, n_obs=3),
     "MPETarget": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
+    "MPECorridor": env_np.EnvCfg(env_np.MPE_CORRIDOR, n=5, n_obs=2, area=1.0, obs_radius=0.2),
     "LidarSpread_noobs": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
     "crowded": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=24, n_obs=12),
 }

@@ -22,6 +22,7 @@ CONFIGS = {   # BASELINE.json configs at test sizes (b small), + edge cases
     "one_agent": env_np.EnvCfg(env_np.LIDAR_TARGET, n=1, n_obs=1),
     "rays48": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=5, n_obs=3, n_rays=48, top_k=8),
     "mpe_target": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
+    "mpe_corridor": env_np.EnvCfg(env_np.MPE_CORRIDOR, n=5, n_obs=2, area=1.0, obs_radius=0.2),
     # n > 16: the one-graph-per-tile GNN kernel (row chunks of 16, ragged last chunk)
     "n24": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=24, n_obs=5),
     "mpe20": env_np.EnvCfg(env_np.MPE_SPREAD, n=20, n_obs=3),

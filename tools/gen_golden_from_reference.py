@@ -32,6 +32,7 @@ CASES = {   # name -> (module, class, n_agents, n_obs, n_envs, n_steps)
     "MPESpread_n8_obs3": ("dgppo.env.mpe.mpe_spread", "MPESpread", 8, 3, 4, 5),
     "LidarSpread_n4_obs0": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 4, 0, 3, 4),
     "MPETarget_n6_obs3": ("dgppo.env.mpe.mpe_target", "MPETarget", 6, 3, 4, 5),
+    "MPECorridor_n5_obs2": ("dgppo.env.mpe.mpe_corridor", "MPECorridor", 5, 2, 4, 5),
 }
 GRAPH_FIELDS = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
 
