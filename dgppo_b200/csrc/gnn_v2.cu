@@ -174,21 +174,21 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
     ef[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sv[j] >= 0) {
       const float* xp = X + (size_t)sv[j] * XS;
-      float acc[H];
+      float acc[H], acd[H];                       // two partial sums per head: half the dependent-FMA depth
 #pragma unroll
-      for (int h = 0; h < H; ++h) acc[h] = qrow[h * QTS + IN];
+      for (int h = 0; h < H; ++h) { acc[h] = qrow[h * QTS + IN]; acd[h] = 0.f; }
 #pragma unroll
       for (int c = 0; c < INX; c += 4) {
         const float4 xv = *reinterpret_cast<const float4*>(xp + c);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           const float4 qv = *reinterpret_cast<const float4*>(qrow + h * QTS + c);
-          acc[h] = fmaf(qv.x, xv.x, acc[h]); acc[h] = fmaf(qv.y, xv.y, acc[h]);
-          acc[h] = fmaf(qv.z, xv.z, acc[h]); acc[h] = fmaf(qv.w, xv.w, acc[h]);
+          acc[h] = fmaf(qv.x, xv.x, acc[h]); acd[h] = fmaf(qv.y, xv.y, acd[h]);
+          acc[h] = fmaf(qv.z, xv.z, acc[h]); acd[h] = fmaf(qv.w, xv.w, acd[h]);
         }
       }
 #pragma unroll
-      for (int h = 0; h < H; ++h) sc[j][h] = acc[h] * isd;
+      for (int h = 0; h < H; ++h) sc[j][h] = (acc[h] + acd[h]) * isd;
       const int e = (t < n) ? i_agent * n + t
                             : ((t < n + n_ag) ? n * n + i_agent * n_ag + (t - n)
                                               : n * n + n * n_ag + i_agent * n_ao + (t - n - n_ag));
@@ -243,12 +243,25 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
     const int c = lane % INX, tq = lane / INX;
     const int eh = (lane >> 2) % H, ej = lane & 3;    // lanes < 12: (head, edge feature)
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, ae = 0.f;
-    for (int t = tq; t < count; t += NG) {
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, be = 0.f;   // second set of partial sums: two list entries in flight
+    int t = tq;
+    for (; t + NG < count; t += 2 * NG) {
+      const float4 av = al[t], bv = al[t + NG];
+      const float x = X[__float_as_int(av.w) + c], y = X[__float_as_int(bv.w) + c];
+      a0 = fmaf(av.x, x, a0); a1 = fmaf(av.y, x, a1); a2 = fmaf(av.z, x, a2);
+      b0 = fmaf(bv.x, y, b0); b1 = fmaf(bv.y, y, b1); b2 = fmaf(bv.z, y, b2);
+      if (NG == 1) {
+        ae = fmaf(scr[t * 4 + eh], scr[J * 32 * 4 + t * 4 + ej], ae);
+        be = fmaf(scr[(t + 1) * 4 + eh], scr[J * 32 * 4 + (t + 1) * 4 + ej], be);
+      }
+    }
+    if (t < count) {
       const float4 av = al[t];
       const float x = X[__float_as_int(av.w) + c];
       a0 = fmaf(av.x, x, a0); a1 = fmaf(av.y, x, a1); a2 = fmaf(av.z, x, a2);
       if (NG == 1) ae = fmaf(scr[t * 4 + eh], scr[J * 32 * 4 + t * 4 + ej], ae);
     }
+    a0 += b0; a1 += b1; a2 += b2; ae += be;
     if (NG > 1) {
 #pragma unroll
       for (int o = INX; o < 32; o <<= 1) {
