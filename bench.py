@@ -339,9 +339,15 @@ def run_gpu(args):
         Vh, ms_vh = ev_time(lambda: algo._value_record("Vh", ro, None))
         (Qh, Ql), ms_gae = ev_time(lambda: algo.gae(ro.costs, -ro.rewards, Vh, Vl))
         _, ms_cbf = ev_time(lambda: algo.cbf_advantage(Ql, Vl, Vh, 0))
-        prepass = {"ms": {"scan_Vl": ms_vl, "Vh": ms_vh, "gae": ms_gae, "cbf_advantage": ms_cbf},
-                   "graphs": b * (T + 1), "note": "one pass over the stochastic record; update() runs Vh + GAE "
-                   "twice (stochastic + deterministic record) and one more deterministic rollout"}
+        try:
+            _, ms_upd = ev_time(lambda: algo.update(ro, 0))
+        except RuntimeError:               # the deterministic rollout resets through the sampler (C5: infeasible area)
+            ms_upd = None
+        prepass = {"ms": {"scan_Vl": ms_vl, "Vh": ms_vh, "gae": ms_gae, "cbf_advantage": ms_cbf,
+                          "update_prepass_total": ms_upd},
+                   "graphs": b * (T + 1), "note": "components: one pass over the stochastic record; update_prepass_total = "
+                   "algo.update(): deterministic rollout (incl. reset) + Vl scan + Vh and GAE on both records + "
+                   "CBF advantage merge (dgppo.py:136-273), no gradient step"}
         del Vl, Vh, Qh, Ql, ro
 
     units = b * T * n * world

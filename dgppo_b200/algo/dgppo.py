@@ -27,7 +27,7 @@ from .. import _lib
 from ..env.base import MultiAgentEnv, ptr, require_cuda, stream_ptr
 from ..env.envs import check_reset
 from ..trainer.data import Rollout
-from ..trainer.rollout import RNN_DIM, run_rollout, run_rollout_chunked
+from ..trainer.rollout import RNN_DIM, RolloutRecord, run_rollout, run_rollout_chunked
 from ..utils.graph import GraphsTuple
 from . import params as P
 from .base import Algorithm
@@ -92,6 +92,7 @@ class DGPPO(Algorithm):
         self._gen.manual_seed(seed)
         self._np_rng = np.random.default_rng(seed)
         self.last_prepass: Optional[dict] = None
+        self._workspaces: dict = {}
         # independent env groups run on separate streams so env kernels overlap policy kernels
         self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "4"))
 
@@ -130,6 +131,15 @@ class DGPPO(Algorithm):
         return buf
 
     # ------------------------------------------------------------------ helpers
+    def _cached(self, name: str, key, make):
+        """Workspace reused across update() calls (multi-GB buffers: allocating them per call costs more
+        than the kernels that fill them).  One entry per name; rebuilt when the shape key changes."""
+        ent = self._workspaces.get(name)
+        if ent is None or ent[0] != key:
+            ent = (key, make())
+            self._workspaces[name] = ent
+        return ent[1]
+
     def _eps_from_key(self, key, shape) -> torch.Tensor:
         g = torch.Generator(device=self.device)
         k = np.asarray(key.detach().cpu() if isinstance(key, torch.Tensor) else key).astype(np.uint64).ravel()
@@ -197,6 +207,10 @@ class DGPPO(Algorithm):
         fresh = graph0 is None
         if fresh:
             graph0 = self._env.reset(b_key, defer_check=True)
+        if record is None:       # update() calls this every step: keep one deterministic record instead of re-allocating GBs
+            record = self._cached("det_record", (graph0.nodes.shape[0], self._env.max_episode_steps),
+                                  lambda: RolloutRecord(self._env, graph0.nodes.shape[0], self._env.max_episode_steps,
+                                                        graph0.nodes.device, stochastic=False))
         ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
                                  self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True,
                                  n_chunks=self.rollout_chunks)
@@ -233,14 +247,16 @@ class DGPPO(Algorithm):
         n = self.n_agents
         nodes, edges, recv, send = self._record_arrays(rollout)
         # carries: t < T as stored; final: act(next_graph[-1], rnn_states[-1]) -> its new carry
-        rnn_rec = torch.empty((b, T + 1, n, RNN_DIM), dtype=torch.float32, device=nodes.device)
+        rnn_rec = self._cached("vh_rnn_rec", (b, T, n),
+                               lambda: torch.empty((b, T + 1, n, RNN_DIM), dtype=torch.float32, device=nodes.device))
         rnn_rec[:, :T] = rollout.rnn_states.reshape(b, T, n, RNN_DIM)
         last = GraphsTuple(*[t[:, -1] if isinstance(t, torch.Tensor) else None for t in rollout.next_graph])
         _, _, final_carry = self._policy_call(last, rollout.rnn_states[:, -1].reshape(b, n, RNN_DIM), None, params)
         rnn_rec[:, T] = final_carry
         nc = self._env.n_cost
         Vh = torch.empty((b, T + 1, n, nc), dtype=torch.float32, device=nodes.device)
-        scratch = torch.empty_like(rnn_rec)     # rnn_out: the kernels' scratch rows (new carry is unused for Vh)
+        # rnn_out: the kernels' scratch rows (the new carry is unused for Vh)
+        scratch = self._cached("vh_scratch", (b, T, n), lambda: torch.empty_like(rnn_rec))
         cfg = self._env.env_cfg()
         _lib.check(_lib.lib().dgppo_gnn_value(
             stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
