@@ -42,3 +42,11 @@ def host():
     batch_idx = np.array(np.array_split(idx, idx.shape[0] // (algo.batch_size // T)))
     return float(A[3].float().mean())
 tm("host part", host, 1)
+print("--- update() repeated")
+for i in range(4):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); algo.update(ro, 0); t1 = time.perf_counter()
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"update call {i}: host returned after {(t1 - t0) * 1e3:.1f} ms, device done after {(t2 - t0) * 1e3:.1f} ms")
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable(); algo.update(ro, 0); torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
