@@ -97,6 +97,8 @@ int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out);
  * sampler get_node_goal_rng (env/utils.py:139-244: <= 1024 tries per agent / goal,
  * restart from agent 0 on failure, unplaced slots repel from the origin).  The
  * caller then runs dgppo_lidar + dgppo_build_graph on the result, as reset does.
+ * MPECorridor (mpe_corridor.py:39-54): agents / goals sampled in [0, area] x [0, side_length_y],
+ * goals then shifted past the corridor, the two obstacles at their fixed places (no draws).
  *   keys      (b) u64 : one key per environment; draw c of key k is
  *             splitmix64(k + c * 0x9E3779B97F4A7C15) -> two 24-bit uniforms (jax's
  *             threefry streams are not reproduced; the accept / reject rules are)
@@ -150,6 +152,7 @@ int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg,
  * get_graph + edge_blocks + EdgeBlock.make_edges + GetGraph.to_padded
  * (lidar_env/base.py:227-271, mpe/base.py:211-241, lidar_spread.py:57-96,
  * lidar_target.py:57-96, lidar_bicycle_target.py:113-118, mpe_spread.py:51-81,
+ * mpe_target.py:51-80, mpe_corridor.py:69-98,
  * utils/graph.py:35-44,212-247).  Outputs are the GraphsTuple array fields
  * (utils/graph.py:61-86) for slot `t` of a (b, pitch, ...) record:
  *   nodes (N, node_dim) f32, edges (E, 4) f32, states (N, state_dim) f32,
