@@ -40,7 +40,7 @@ class DgppoNetLayout(C.Structure):
                                           "total")])
 
 
-ABI_VERSION = 3        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
+ABI_VERSION = 4        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
 
 _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 
@@ -48,7 +48,7 @@ _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 class DgppoRolloutBuffers(C.Structure):
     _fields_ = [(k, _fp) for k in ("nodes", "edges", "states", "receivers", "senders", "node_type",
                                    "n_node", "n_edge", "rnn", "eps", "actions", "log_pis", "rewards",
-                                   "costs", "agent_ws", "hits_ws", "goal", "obstacles", "ray_dirs")]
+                                   "costs", "agent_ws", "hits_ws", "goal", "obstacles", "ray_dirs", "hits_ws2")]
 
 
 NET_POLICY, NET_VH, NET_VL = 0, 1, 2

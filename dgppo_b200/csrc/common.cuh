@@ -80,6 +80,11 @@ __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
   return d;
 }
 
+// K2 with predict = 1 casts the rays from the position the agents will have AFTER the coming step
+// (computed from the current state, which is all it depends on); dgppo_lidar is predict = 0.
+int launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent, const float* obstacles,
+                 const float* ray_dirs, float* hits, int32_t b, int predict);
+
 inline int check_env_cfg(const DgppoEnvCfg* c) {
   if (!c) return DGPPO_EINVAL;
   if (c->kind < 0 || c->kind > 5) return DGPPO_ENOTSUP;

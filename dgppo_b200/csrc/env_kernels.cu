@@ -41,6 +41,24 @@ static EnvConsts make_consts(const DgppoEnvCfg& c) {
   return k;
 }
 
+// Next position of one agent (the first two components of agent_step_euler + clip_state).  It depends on
+// the CURRENT state only - the action moves the velocity / heading, not the position - which is what lets
+// the LiDAR of step t + 1 run ahead of the policy of step t (rollout.cu).  K1 and K2 both call this, so the
+// bits agree.
+__device__ __forceinline__ void next_position(const EnvConsts& k, const float* s, int sd, float& x, float& y) {
+  float ox, oy;
+  if (sd == 5) {                                             // lidar_bicycle_target.py:96-103
+    const float theta = atan2f(s[3], s[2]);
+    ox = fadd(s[0], fmul(fmul(s[4], cosf(theta)), k.dt));
+    oy = fadd(s[1], fmul(fmul(s[4], sinf(theta)), k.dt));
+  } else {                                                   // lidar_env/base.py:146-147
+    ox = fadd(fmul(s[2], k.dt), s[0]);
+    oy = fadd(fmul(s[3], k.dt), s[1]);
+  }
+  x = clampf(ox, k.lo[0], k.hi[0]);
+  y = clampf(oy, k.lo[1], k.hi[1]);
+}
+
 // ------------------------------------------------------------------- K1
 // One warp per environment; lanes stride over agents / goals.
 constexpr int K1_WARPS = 4;
@@ -77,18 +95,15 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
     if (sd == 5) {                                           // lidar_bicycle_target.py:96-106
       const float theta = atan2f(s[3], s[2]);
       const float theta_next = fadd(theta, fmul(fmul(fmul(s[4], a0), k.dt), 10.f));
-      o[0] = fadd(s[0], fmul(fmul(s[4], cosf(theta)), k.dt));
-      o[1] = fadd(s[1], fmul(fmul(s[4], sinf(theta)), k.dt));
       o[2] = cosf(theta_next);
       o[3] = sinf(theta_next);
       o[4] = fadd(s[4], fmul(fmul(a1, k.dt), 10.f));
     } else {                                                 // lidar_env/base.py:146-147
-      o[0] = fadd(fmul(s[2], k.dt), s[0]);
-      o[1] = fadd(fmul(s[3], k.dt), s[1]);
       o[2] = fadd(fmul(fmul(a0, 10.f), k.dt), s[2]);
       o[3] = fadd(fmul(fmul(a1, 10.f), k.dt), s[3]);
     }
-    for (int c = 0; c < sd; ++c) nx[i * sd + c] = clampf(o[c], k.lo[c], k.hi[c]);
+    next_position(k, s, sd, nx[i * sd + 0], nx[i * sd + 1]);
+    for (int c = 2; c < sd; ++c) nx[i * sd + c] = clampf(o[c], k.lo[c], k.hi[c]);
   }
   __syncwarp();
 
@@ -224,7 +239,7 @@ __device__ __forceinline__ void lidar_slot_near(float dx12, float dy12, float dx
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ obstacles,
-             const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd) {
+             const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd, int predict) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long item = (long)blockIdx.x * K2_WARPS + warp;
@@ -240,7 +255,12 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   float* hx = reinterpret_cast<float*>(key + R);                // [R]
   float* hy = hx + R;
 
-  const float x1 = agent[item * sd + 0], y1 = agent[item * sd + 1];
+  float x1 = agent[item * sd + 0], y1 = agent[item * sd + 1];
+  if (predict) {                      // agent holds the state BEFORE the step: cast from where it will be after it
+    float s[5];
+    for (int c = 0; c < sd; ++c) s[c] = agent[item * sd + c];
+    next_position(k, s, sd, x1, y1);
+  }
   const float* ob = obstacles + (size_t)env * k.n_obs * DGPPO_OBS_STRIDE;
 
   // inside_obstacles(start, r=0): obstacle.py:62-72 with r = 0 reduces to
@@ -503,6 +523,11 @@ extern "C" int dgppo_env_step(void* stream, const DgppoEnvCfg* cfg, const float*
 
 extern "C" int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent,
                            const float* obstacles, const float* ray_dirs, float* hits, int32_t b) {
+  return dgppo::launch_lidar(stream, cfg, agent, obstacles, ray_dirs, hits, b, 0);
+}
+
+int dgppo::launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent, const float* obstacles,
+                        const float* ray_dirs, float* hits, int32_t b, int predict) {
   if (int rc = check_env_cfg(cfg)) return rc;
   if (!is_lidar(cfg->kind) || cfg->n_obs == 0) return DGPPO_ENOTSUP;
   if (b == 0) return 0;
@@ -514,7 +539,7 @@ extern "C" int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg, const float* ag
   const long items = (long)b * k.n;
   const int grid = (int)((items + K2_WARPS - 1) / K2_WARPS);
   lidar_kernel<<<grid, K2_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4);
+      k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4, predict);
   return (int)cudaGetLastError();
 }
 

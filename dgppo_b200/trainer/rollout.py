@@ -11,6 +11,7 @@ T+1 graphs once and exposes `graph` / `next_graph` as two views of it.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -22,6 +23,15 @@ from ..utils.graph import GraphsTuple
 from .data import Rollout
 
 RNN_DIM = 64
+
+_POOLS = {}
+
+
+def _submit_pool(n: int):
+    from concurrent.futures import ThreadPoolExecutor
+    if n not in _POOLS:
+        _POOLS[n] = ThreadPoolExecutor(max_workers=n, thread_name_prefix="dgppo-rollout")
+    return _POOLS[n]
 
 
 class RolloutRecord:
@@ -49,9 +59,10 @@ class RolloutRecord:
         self.costs = torch.empty((b, T, n, 2), **f32)
         self.dones = torch.zeros((b, T), dtype=torch.bool, device=device)
         self.agent_ws = torch.empty((2, b, n, d.state_dim), **f32)
-        self.hits_ws = None
+        self.hits_ws = self.hits_ws2 = None
         if isinstance(env, LidarEnv) and d.n_obs_nodes > 0:
             self.hits_ws = torch.empty((b, n, env.params["top_k_rays"], 2), **f32)
+            self.hits_ws2 = torch.empty_like(self.hits_ws)      # second buffer: LiDAR look-ahead (dgppo_rollout)
 
     def nbytes(self) -> int:
         ts = [self.nodes, self.edges, self.states, self.receivers, self.senders, self.node_type,
@@ -61,7 +72,7 @@ class RolloutRecord:
         return sum(t.numel() * t.element_size() for t in ts)
 
     _TENSORS = ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge", "rnn",
-                "actions", "log_pis", "rewards", "costs", "dones", "hits_ws")
+                "actions", "log_pis", "rewards", "costs", "dones", "hits_ws", "hits_ws2")
 
     def env_slice(self, lo: int, hi: int) -> "RolloutRecord":
         """A view of environments [lo, hi) of this record (shares memory)."""
@@ -129,7 +140,7 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
         ptr(rec.nodes), ptr(rec.edges), ptr(rec.states), ptr(rec.receivers), ptr(rec.senders),
         ptr(rec.node_type), ptr(rec.n_node), ptr(rec.n_edge), ptr(rec.rnn), ptr(eps),
         ptr(rec.actions), ptr(rec.log_pis) if eps is not None else None, ptr(rec.rewards), ptr(rec.costs),
-        ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays))
+        ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays), ptr(rec.hits_ws2))
     cfg = env.env_cfg()
     _lib.check(_lib.lib().dgppo_rollout(stream_ptr(), C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
                                          C.byref(buf), T, b, prof), "dgppo_rollout")
@@ -178,7 +189,9 @@ def run_rollout_chunked(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state
     cur = torch.cuda.current_stream(dev)
     start = torch.cuda.Event()
     start.record(cur)
-    for i, (lo, hi, sub, st) in enumerate(record._chunks):
+    def submit(i):
+        lo, hi, sub, st = record._chunks[i]
+        torch.cuda.set_device(dev)
         st.wait_event(start)
         with torch.cuda.stream(st):
             g0 = graph0.map_arrays(lambda t: t[lo:hi])._replace(env_states=_slice_env_states(graph0.env_states, lo, hi))
@@ -186,6 +199,18 @@ def run_rollout_chunked(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state
                         sub, test_mode, prof if i == 0 else None)
         done = torch.cuda.Event()
         done.record(st)
+        return done
+
+    # DGPPO_ROLLOUT_THREADS=1: one submitting thread per env group (the launch sequence of a group is a C
+    # loop that releases the GIL), so the groups' kernels enter their streams side by side instead of one
+    # group after the other.  Only matters when submission is slow (e.g. with DGPPO_LIDAR_AHEAD=1, whose
+    # cross-stream events triple the host cost per step); measured +-0 otherwise, so off by default.
+    if os.environ.get("DGPPO_ROLLOUT_THREADS", "0") == "1":
+        pool = _submit_pool(n_chunks)
+        dones = list(pool.map(submit, range(n_chunks)))
+    else:
+        dones = [submit(i) for i in range(n_chunks)]
+    for done in dones:
         cur.wait_event(done)
     rec, n, es = record, env.num_agents, graph0.env_states
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DGPPO_ABI_VERSION 3
+#define DGPPO_ABI_VERSION 4
 
 /* negative error codes (positive values are cudaError_t) */
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
@@ -308,7 +308,10 @@ int dgppo_cbf_advantage(void* stream, const float* Ql, const float* Vl, const fl
  * (NULL allowed iff eps NULL), rewards (b,T), costs (b,T,n,2).
  * agent_ws: workspace (2, b, n, state_dim) ping-pong agent states, slot 0
  * initialised by the caller; hits_ws (b, n, top_k, 2) (Lidar) initialised
- * with the hits of the initial state.                                        */
+ * with the hits of the initial state.  hits_ws2 (same shape, nullable): with a
+ * second hit buffer the LiDAR of step t + 1 - which depends on the state before
+ * step t only, the action never moves the position within a step - runs on an
+ * internal side stream concurrently with the policy forward of step t.         */
 typedef struct DgppoRolloutBuffers {
   float* nodes; float* edges; float* states;
   int32_t* receivers; int32_t* senders; int32_t* node_type;
@@ -317,6 +320,7 @@ typedef struct DgppoRolloutBuffers {
   float* actions; float* log_pis; float* rewards; float* costs;
   float* agent_ws; float* hits_ws;
   const float* goal; const float* obstacles; const float* ray_dirs;
+  float* hits_ws2;
 } DgppoRolloutBuffers;
 
 int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,

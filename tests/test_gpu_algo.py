@@ -207,3 +207,28 @@ def test_rollout_writes_stay_inside_the_record(name, b, T):
             assert (inner != SI).all(), f"{key}: elements left unwritten"
         else:
             assert not np.isnan(inner).any(), f"{key}: elements left unwritten (or NaN produced)"
+
+
+@pytest.mark.parametrize("env_id,n,obs", [("LidarSpread", 8, 8), ("LidarBicycleTarget", 4, 3)])
+def test_lidar_look_ahead_schedule_is_bit_identical(env_id, n, obs, monkeypatch):
+    """DGPPO_LIDAR_AHEAD=1 casts the rays of graph t+1 from the predicted position on a side stream while the
+    policy of step t runs (and DGPPO_ROLLOUT_THREADS=1 submits the env groups from threads): same record bits."""
+    from dgppo_b200.algo import make_algo
+    from dgppo_b200.env import make_env
+    b, T = 64, 12
+    env = make_env(env_id, num_agents=n, num_obs=obs, max_step=T)
+    algo = make_algo("dgppo", env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
+                     action_dim=env.action_dim, n_agents=n, batch_size=b * T, seed=2)
+    g0 = env.reset(np.arange(b, dtype=np.uint64) + 50)
+    eps = torch.randn((b, T, n, 2), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    ref = algo.collect(algo.params, None, eps=eps, graph0=g0)
+    ref_t = {k: getattr(ref.next_graph, k).clone() for k in ("nodes", "edges", "states", "receivers", "senders")}
+    ref_a, ref_c, ref_r = ref.actions.clone(), ref.costs.clone(), ref.rewards.clone()
+    monkeypatch.setenv("DGPPO_LIDAR_AHEAD", "1")
+    monkeypatch.setenv("DGPPO_ROLLOUT_THREADS", "1")
+    for chunks in (1, 4):
+        algo.rollout_chunks = chunks
+        out = algo.collect(algo.params, None, eps=eps, graph0=g0)
+        for k, v in ref_t.items():
+            assert torch.equal(getattr(out.next_graph, k), v), f"{k} (chunks={chunks})"
+        assert torch.equal(out.actions, ref_a) and torch.equal(out.costs, ref_c) and torch.equal(out.rewards, ref_r)
