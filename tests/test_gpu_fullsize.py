@@ -160,3 +160,55 @@ def test_full_size_rollout(name, env_id, n, obs, b, T, n_samples):
             np.testing.assert_allclose(g_n[k], r_next[k], rtol=1e-5, atol=1e-6, err_msg=k)
         else:
             assert_bits_equal(g_n[k], r_next[k], k)
+
+
+def test_full_size_update_prepass():
+    """algo.update() at the headline size (C3: 4096 envs x T=128): Vl scan, Vh over all (b, T+1) graphs of both
+    records, both GAE passes and the CBF advantage merge.  Checked by properties over all entries and by the
+    oracle on sampled environments / slots (dgppo.py:204-273)."""
+    from oracle import algo_np
+    name, env_id, n, obs, b, T, _ = SIZES[1]
+    cfg = CONFIGS[name]
+    env, algo, g0, eps = _setup(env_id, n, obs, b, T, seed=9)
+    ro = algo.collect(algo.params, None, eps=eps, graph0=g0)
+    info = algo.update(ro, step=0)
+    pp = algo.last_prepass
+    Vl, Vh, Qh, Ql, A = pp["bTp1_Vl"], pp["bTp1ah_Vh"], pp["bTah_Qh"], pp["bT_Ql"], pp["bTa_A"]
+    assert Vl.shape == (b, T + 1) and Vh.shape == (b, T + 1, n, 2) and Qh.shape == (b, T, n, 2) and A.shape == (b, T, n)
+    for t in (Vl, Vh, Qh, Ql, A, pp["bTp1ah_Vh_det"], pp["bTah_Qh_det"]):
+        assert bool(torch.isfinite(t).all())
+    assert 0.0 <= info["eval/safe_data"] <= 1.0
+    # Qh is a lambda-mix of running maxima over the costs (of any component: the recursion takes max_h h_t) and
+    # the bootstrap values: bounded by their extremes per (environment, agent)
+    hi = torch.maximum(ro.costs.amax(dim=(1, 3)), Vh.amax(dim=(1, 3)))            # (b, n)
+    lo = torch.minimum(ro.costs.amin(dim=(1, 3)), Vh.amin(dim=(1, 3)))
+    assert bool((Qh <= hi[:, None, :, None] + 1e-4).all()) and bool((Qh >= lo[:, None, :, None] - 1e-4).all())
+
+    rng = np.random.default_rng(3)
+    envs = rng.integers(0, b, 4)
+    # GAE and advantage merge: full trajectories of a few environments through the oracle
+    for e in envs:
+        rQh, rQl = algo_np.compute_dec_ocp_gae(ro.costs[e].cpu().numpy(), -ro.rewards[e].cpu().numpy(),
+                                               Vh[e].cpu().numpy(), Vl[e].cpu().numpy(), 0.99, 0.95)
+        np.testing.assert_allclose(Qh[e].cpu().numpy(), rQh, rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(Ql[e].cpu().numpy(), rQl, rtol=1e-5, atol=5e-6)
+    sel = torch.as_tensor(envs, device=Vl.device)
+    rA, rd, _, rsafe = algo_np.cbf_advantage(Ql[sel].cpu().numpy(), Vl[sel].cpu().numpy(), Vh[sel].cpu().numpy(),
+                                             env.dt, algo.alpha, algo.cbf_eps,
+                                             algo.cbf_schedule_fn(0) if algo.cbf_schedule else algo.cbf_weight)
+    near = (np.abs(rd) < 1e-4).any(-1)                       # is_safe flips on a sign: skip entries at the threshold
+    np.testing.assert_allclose(A[sel].cpu().numpy()[~near], rA[~near], rtol=1e-4, atol=1e-4)
+    # Vh on sampled (environment, slot) pairs; Vl by replaying the recurrent scan of two environments
+    se = torch.as_tensor(rng.integers(0, b, 48), device=Vl.device)
+    st = torch.as_tensor(rng.integers(0, T, 48), device=Vl.device)
+    g_t = {k: getattr(ro.graph, k)[se, st].cpu().numpy() for k in GRAPH_FIELDS}
+    rnn_t = ro.rnn_states.reshape(b, T, n, 64)[se, st].cpu().numpy()
+    rVh = nn_np.vh_forward(algo.params["Vh"], g_t, rnn_t, n)
+    np.testing.assert_allclose(Vh[se, st].cpu().numpy(), rVh, rtol=1e-5, atol=1e-5)
+    two = torch.as_tensor(envs[:2], device=Vl.device)
+    h = np.zeros((2, 64), F)
+    for t in range(T + 1):
+        src, tt = (ro.graph, t) if t < T else (ro.next_graph, T - 1)
+        gt = {k: getattr(src, k)[two, tt].cpu().numpy() for k in GRAPH_FIELDS}
+        v, h = nn_np.vl_forward(algo.params["Vl"], gt, h, n)
+        np.testing.assert_allclose(Vl[two, t].cpu().numpy(), v, rtol=5e-5, atol=5e-5, err_msg=f"Vl t={t}")
