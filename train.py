@@ -52,51 +52,44 @@ def train(args):
     trainer.train()
 
 
+# The reference CLI (train.py:134-181), flag for flag: (flags, type or None for a switch, default | REQUIRED)
+REQUIRED = object()
+CLI = [
+    # what to run
+    (("--env",), str, REQUIRED), (("-n", "--num-agents"), int, REQUIRED), (("--algo",), str, REQUIRED),
+    (("--obs",), int, REQUIRED),
+    # run control, algorithm coefficients
+    (("--seed",), int, 0), (("--steps",), int, 200000), (("--name",), str, None), (("--debug",), None, False),
+    (("--cost-weight",), float, 0.0), (("--n-rays",), int, 32), (("--full-observation",), None, False),
+    (("--clip-eps",), float, 0.25), (("--lagr-init",), float, 0.5), (("--lr-lagr",), float, 1e-7),
+    (("--cbf-weight",), float, 1.0), (("--cbf-eps",), float, 1e-2), (("--alpha",), float, 10.0),
+    (("--no-cbf-schedule",), None, False), (("--cost-schedule",), None, False), (("--no-rnn",), None, False),
+    # networks
+    (("--actor-gnn-layers",), int, 2), (("--Vl-gnn-layers",), int, 2), (("--Vh-gnn-layers",), int, 1),
+    (("--lr-actor",), float, 3e-4), (("--lr-Vl",), float, 1e-3), (("--lr-Vh",), float, 1e-3),
+    (("--rnn-layers",), int, 1), (("--use-lstm",), None, False), (("--coef-ent",), float, 1e-2),
+    (("--rnn-step",), int, 16),
+    # sizes, logging
+    (("--n-env-train",), int, 128), (("--batch-size",), int, 16384), (("--n-env-test",), int, 32),
+    (("--log-dir",), str, "./logs"), (("--eval-interval",), int, 50), (("--eval-epi",), int, 1),
+    (("--save-interval",), int, 50),
+]
+
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="DGPPO training on the B200 rollout kernels")
+    for flags, typ, default in CLI:
+        if typ is None:
+            parser.add_argument(*flags, action="store_true", default=default)
+        elif default is REQUIRED:
+            parser.add_argument(*flags, type=typ, required=True)
+        else:
+            parser.add_argument(*flags, type=typ, default=default)
+    return parser
+
+
 def main():
-    parser = argparse.ArgumentParser()
-    # required arguments
-    parser.add_argument("--env", type=str, required=True)
-    parser.add_argument("-n", "--num-agents", type=int, required=True)
-    parser.add_argument("--algo", type=str, required=True)
-    parser.add_argument("--obs", type=int, required=True)
-    # custom arguments
-    parser.add_argument("--seed", type=int, default=0)
-    parser.add_argument("--steps", type=int, default=200000)
-    parser.add_argument("--name", type=str, default=None)
-    parser.add_argument("--debug", action="store_true", default=False)
-    parser.add_argument("--cost-weight", type=float, default=0.)
-    parser.add_argument("--n-rays", type=int, default=32)
-    parser.add_argument('--full-observation', action='store_true', default=False)
-    parser.add_argument('--clip-eps', type=float, default=0.25)
-    parser.add_argument('--lagr-init', type=float, default=0.5)
-    parser.add_argument('--lr-lagr', type=float, default=1e-7)
-    parser.add_argument("--cbf-weight", type=float, default=1.0)
-    parser.add_argument("--cbf-eps", type=float, default=1e-2)
-    parser.add_argument("--alpha", type=float, default=10.0)
-    parser.add_argument("--no-cbf-schedule", action="store_true", default=False)
-    parser.add_argument("--cost-schedule", action="store_true", default=False)
-    parser.add_argument("--no-rnn", action="store_true", default=False)
-    # NN arguments
-    parser.add_argument("--actor-gnn-layers", type=int, default=2)
-    parser.add_argument("--Vl-gnn-layers", type=int, default=2)
-    parser.add_argument("--Vh-gnn-layers", type=int, default=1)
-    parser.add_argument("--lr-actor", type=float, default=3e-4)
-    parser.add_argument("--lr-Vl", type=float, default=1e-3)
-    parser.add_argument("--lr-Vh", type=float, default=1e-3)
-    parser.add_argument("--rnn-layers", type=int, default=1)
-    parser.add_argument("--use-lstm", action="store_true", default=False)
-    parser.add_argument("--coef-ent", type=float, default=1e-2)
-    parser.add_argument("--rnn-step", type=int, default=16)
-    # default arguments
-    parser.add_argument("--n-env-train", type=int, default=128)
-    parser.add_argument("--batch-size", type=int, default=16384)
-    parser.add_argument("--n-env-test", type=int, default=32)
-    parser.add_argument("--log-dir", type=str, default="./logs")
-    parser.add_argument("--eval-interval", type=int, default=50)
-    parser.add_argument("--eval-epi", type=int, default=1)
-    parser.add_argument("--save-interval", type=int, default=50)
-    args = parser.parse_args()
-    train(args)
+    train(build_parser().parse_args())
 
 
 if __name__ == "__main__":
