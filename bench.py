@@ -81,7 +81,7 @@ def cpu_rollout_rate(w, target_s=12.0, seed=0):
     ~target_s.  -> agent-steps/s (all workers, wall clock), sample description, workers."""
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
-    workers = max(1, os.cpu_count() or 1)
+    workers = max(1, min(os.cpu_count() or 1, 64))      # one process per core; capped so start-up stays short
     n = w["n"]
     b, T = 8, 4
     rate, sample = 0.0, ""

@@ -108,6 +108,6 @@ def test_bench_reference_arm_contract():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "agent-steps/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == min(os.cpu_count() or 1, 64)
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["higher_is_better"] is True and "workload" in line["config"]
