@@ -245,7 +245,8 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   const long item = (long)blockIdx.x * K2_WARPS + warp;
   const int n = k.n, R = k.n_rays, ne = k.n_obs * 4;
   if (item >= (long)b * n) return;
-  const int env = (int)(item / n);
+  // (b * n fits 32 bits whenever the grid does: the launcher's grid is an int)
+  const int env = (int)((unsigned)item / (unsigned)n);
   const int per_warp = ne * 5 + ((ne + 3) & ~3) + 4 * R;        // floats (see the host launcher)
   float* base = smem + (size_t)warp * per_warp;
   float4* ed = reinterpret_cast<float4*>(base);                 // [ne] (dx43, dy43, dx13, dy13)
@@ -537,6 +538,7 @@ int dgppo::launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent
   const size_t smem = (size_t)K2_WARPS * (ne * 5 + ((ne + 3) & ~3) + 4 * k.n_rays) * sizeof(float);
   if (smem > 48 * 1024) return DGPPO_ENOTSUP;
   const long items = (long)b * k.n;
+  if (items > 0x7fffffffL) return DGPPO_ENOTSUP;
   const int grid = (int)((items + K2_WARPS - 1) / K2_WARPS);
   lidar_kernel<<<grid, K2_WARPS * 32, smem, (cudaStream_t)stream>>>(
       k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4, predict);
