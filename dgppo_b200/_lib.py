@@ -37,10 +37,10 @@ class DgppoNetLayout(C.Structure):
     _fields_ = ([(k, C.c_int32 * 2) for k in ("wqk", "wagg", "wu", "bu", "wq", "bq", "wkt", "in_dim", "out_dim")] +
                 [(k, C.c_int32) for k in ("d0w", "d0b", "ln0s", "ln0b", "d1w", "d1b", "ln1s", "ln1b",
                                           "wi", "bi", "wh", "bhn", "out_w", "out_b",
-                                          "total")])
+                                          "tc_head", "total")])
 
 
-ABI_VERSION = 4        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
+ABI_VERSION = 5        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
 
 _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 

@@ -87,7 +87,7 @@ class DGPPO(Algorithm):
             "Vh": P.init_value_params(node_dim, edge_dim, env.n_cost, Vh_gnn_layers, seed=seed + 2),
         }
         self._cfgs = {"policy": self.policy_cfg, "Vl": self.Vl_cfg, "Vh": self.Vh_cfg}
-        self._packed: Dict[Tuple[str, int], torch.Tensor] = {}
+        self._packed: Dict[str, tuple] = {}
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed)
         self._np_rng = np.random.default_rng(seed)
@@ -116,29 +116,50 @@ class DGPPO(Algorithm):
         return {"policy": self._trees["policy"], "Vl": self._trees["Vl"], "Vh": self._trees["Vh"]}
 
     def set_params(self, name: str, tree: dict) -> None:
+        """Replace the pytree of net `name`; its packed device copy is rebuilt on next use."""
         self._trees[name] = tree
+        self._packed.pop(name, None)
+
+    def invalidate(self, name: Optional[str] = None) -> None:
+        """Drop the packed device copy of `name` (all nets when None).  Needed only after editing the NumPy
+        leaves of a pytree IN PLACE: the cache is keyed on pytree identity and cannot see such edits."""
+        if name is None:
+            self._packed.clear()
+        else:
+            self._packed.pop(name, None)
 
     def packed(self, name: str, params: Optional[dict] = None) -> torch.Tensor:
-        """Device buffer of net `name` for the given params pytree (cached per pytree object)."""
+        """Device buffer of net `name` for the given params pytree.  One cached entry per net, holding a
+        reference to the pytree it was packed from and compared with `is` (an `id()` key could be reused by
+        a later pytree once the earlier one is freed)."""
         tree = (self.params if params is None else params)[name]
-        key = (name, id(tree))
-        buf = self._packed.get(key)
-        if buf is None:
-            if len(self._packed) > 16:
-                self._packed.clear()
-            buf = torch.from_numpy(P.pack_params(tree, self._cfgs[name])).to(self.device)
-            self._packed[key] = buf
-        return buf
+        ent = self._packed.get(name)
+        if ent is None or ent[0] is not tree:
+            ent = (tree, torch.from_numpy(P.pack_params(tree, self._cfgs[name])).to(self.device))
+            self._packed[name] = ent
+        return ent[1]
 
     # ------------------------------------------------------------------ helpers
     def _cached(self, name: str, key, make):
         """Workspace reused across update() calls (multi-GB buffers: allocating them per call costs more
-        than the kernels that fill them).  One entry per name; rebuilt when the shape key changes."""
-        ent = self._workspaces.get(name)
-        if ent is None or ent[0] != key:
-            ent = (key, make())
-            self._workspaces[name] = ent
-        return ent[1]
+        than the kernels that fill them).  One entry per (name, shape key): the train and the evaluation
+        shapes each keep theirs, so alternating between them neither reallocates nor lets one overwrite the
+        other.  NOTE the returned tensors alias the workspace: a later call with the same shape key
+        overwrites them (copy what must outlive the next update / evaluation)."""
+        ent = self._workspaces.get((name, key))
+        if ent is None:
+            if sum(1 for k in self._workspaces if k[0] == name) >= 3:        # bound the number of live shapes
+                for k in [k for k in self._workspaces if k[0] == name]:
+                    del self._workspaces[k]
+            ent = make()
+            self._workspaces[(name, key)] = ent
+        return ent
+
+    def _shape_key(self, b: int):
+        """Everything a record / workspace size depends on: batch, horizon and the env's graph dimensions."""
+        d = self._env.graph_dims()
+        return (b, self._env.max_episode_steps, self.n_agents, d.n_nodes, d.n_edges, d.node_dim, d.state_dim,
+                self._env.n_cost)
 
     def _eps_from_key(self, key, shape) -> torch.Tensor:
         g = torch.Generator(device=self.device)
@@ -208,7 +229,7 @@ class DGPPO(Algorithm):
         if fresh:
             graph0 = self._env.reset(b_key, defer_check=True)
         if record is None:       # update() calls this every step: keep one deterministic record instead of re-allocating GBs
-            record = self._cached("det_record", (graph0.nodes.shape[0], self._env.max_episode_steps),
+            record = self._cached("det_record", self._shape_key(graph0.nodes.shape[0]),
                                   lambda: RolloutRecord(self._env, graph0.nodes.shape[0], self._env.max_episode_steps,
                                                         graph0.nodes.device, stochastic=False))
         ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
@@ -247,7 +268,7 @@ class DGPPO(Algorithm):
         n = self.n_agents
         nodes, edges, recv, send = self._record_arrays(rollout)
         # carries: t < T as stored; final: act(next_graph[-1], rnn_states[-1]) -> its new carry
-        rnn_rec = self._cached("vh_rnn_rec", (b, T, n),
+        rnn_rec = self._cached("vh_rnn_rec", self._shape_key(b),
                                lambda: torch.empty((b, T + 1, n, RNN_DIM), dtype=torch.float32, device=nodes.device))
         rnn_rec[:, :T] = rollout.rnn_states.reshape(b, T, n, RNN_DIM)
         last = GraphsTuple(*[t[:, -1] if isinstance(t, torch.Tensor) else None for t in rollout.next_graph])
@@ -256,7 +277,7 @@ class DGPPO(Algorithm):
         nc = self._env.n_cost
         Vh = torch.empty((b, T + 1, n, nc), dtype=torch.float32, device=nodes.device)
         # rnn_out: the kernels' scratch rows (the new carry is unused for Vh)
-        scratch = self._cached("vh_scratch", (b, T, n), lambda: torch.empty_like(rnn_rec))
+        scratch = self._cached("vh_scratch", self._shape_key(b), lambda: torch.empty_like(rnn_rec))
         cfg = self._env.env_cfg()
         _lib.check(_lib.lib().dgppo_gnn_value(
             stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),

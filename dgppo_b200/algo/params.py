@@ -187,7 +187,32 @@ def pack_params(tree: Dict, cfg: _lib.DgppoNetCfg) -> np.ndarray:
     else:
         out_w[:, :cfg.n_out] = _np(p["Dense_0"]["kernel"]); out_b[:cfg.n_out] = _np(p["Dense_0"]["bias"])
     put(L.out_w, out_w); put(L.out_b, out_b)
+    # tensor-core head operands (include/dgppo_abi.h, tc_head): [hi | lo] TF32 split of each matrix in the
+    # K-major canonical layout [K/4][N][4]
+    off = L.tc_head
+    for w in (buf[L.d0w:L.d0w + HID * HID].reshape(HID, HID), buf[L.d1w:L.d1w + HID * HID].reshape(HID, HID),
+              buf[L.wi:L.wi + HID * 3 * HID].reshape(HID, 3 * HID), buf[L.wh:L.wh + HID * 3 * HID].reshape(HID, 3 * HID)):
+        blk = tc_operand(w)
+        buf[off:off + blk.size] = blk
+        off += blk.size
     return buf
+
+
+def tf32_round(x: np.ndarray) -> np.ndarray:
+    """Round fp32 to TF32 (10 explicit mantissa bits), ties away from zero as cvt.rna.tf32.f32 does."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tc_operand(w: np.ndarray) -> np.ndarray:
+    """(K, N) weight -> flat [hi | lo], each [K/4][N][4] with block[kc][n][j] = W[4 kc + j][n]."""
+    w = np.asarray(w, np.float32)
+    K, N = w.shape
+    hi = tf32_round(w)
+    lo = tf32_round(w - hi)
+    def canon(a):
+        return a.reshape(K // 4, 4, N).transpose(0, 2, 1).reshape(-1)
+    return np.concatenate([canon(hi), canon(lo)])
 
 
 def count_params(tree) -> int:

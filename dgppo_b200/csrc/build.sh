@@ -9,6 +9,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
   -Xcompiler -fPIC -shared -I"$root/include" -I"$here" \
   -prec-div=true -prec-sqrt=true "$@" \
-  "$here/env_kernels.cu" "$here/reset_kernels.cu" "$here/gnn_kernels.cu" "$here/gnn_v2.cu" "$here/gae_kernels.cu" "$here/rollout.cu" \
+  "$here/env_kernels.cu" "$here/reset_kernels.cu" "$here/gnn_kernels.cu" "$here/gnn_v2.cu" "$here/head_tc.cu" "$here/gae_kernels.cu" "$here/rollout.cu" \
   -o "$out" -lcudart
 echo "built $out"

@@ -35,6 +35,21 @@ struct GnnArgs {
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
+// Tensor-core head (head_tc.cu): B operands of the 3xTF32 products, hi copy then lo copy, each in the
+// no-swizzle K-major canonical layout [K/4 chunks][n][4]:  block[kc][n][j] = W[4 kc + j][n].
+constexpr int TC_D_FL = 2 * 64 * 64;      // one Dense64 block (floats, hi + lo): 32 KB
+constexpr int TC_G_FL = 2 * 64 * 192;     // one GRU block (x part [ir|iz|in] or h part [hr|hz|hn]): 96 KB
+constexpr int TC_HEAD_FL = 2 * TC_D_FL + 2 * TC_G_FL;   // [Dense0 | Dense1 | GRU x | GRU h] = 256 KB
+
+
+// GRU gate activations on the SFU (ex2.approx / rcp.approx): absolute error below 3e-7 on outputs in
+// (0, 1) / (-1, 1), inside the fp32 tolerance of the path (rtol 1e-5).
+__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) {
+  const float ax = fminf(fabsf(x), 15.f);                  // tanh(15) == 1 in fp32; keeps exp finite
+  const float t = 1.f - __fdividef(2.f, __expf(2.f * ax) + 1.f);
+  return copysignf(t, x);
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
@@ -95,5 +110,9 @@ __device__ __forceinline__ void policy_tail(const GnnArgs& g, float m0, float m1
 // (embeddings expected in rnn_out); 1 and 2 serve the Vl scan, whose GNN part has no recurrence.
 int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const float* params,
                   const GnnArgs& g, int sms, int phase = 0);
+
+// Tensor-core head (head_tc.cu) over the rows of g (embeddings in rnn_out); tcw = params + layout.tc_head.
+int launch_head_tc(cudaStream_t st, const NetP& P, const GnnArgs& g, const float* tcw, int sms, bool pdl);
+size_t head_tc_smem_bytes();
 
 }  // namespace dgppo

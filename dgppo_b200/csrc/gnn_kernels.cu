@@ -474,6 +474,7 @@ static int fill_layout(const DgppoNetCfg* net, DgppoNetLayout* L) {
     L->wq[l] = take(IN * H * D); L->bq[l] = take(H * D);
     L->wkt[l] = take(H * D * round4(IN + 1));
   }
+  L->tc_head = take(TC_HEAD_FL);                           // tensor-core head operands, last
   L->total = off;
   return 0;
 }

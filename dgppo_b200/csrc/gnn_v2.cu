@@ -20,6 +20,7 @@
 // Same arithmetic as v1 (GNN regrouping); attention is parallelised
 // over (row, head, edge slot) instead of (row, head).
 #include <stdlib.h>
+#include <string.h>
 
 #include "gnn_common.cuh"
 
@@ -123,15 +124,6 @@ struct GnnV2Plan {
   int hw_off, hw_fl;      // head weights
   size_t head_smem_bytes;
 };
-
-// GRU gate activations of head_kernel_wide on the SFU (ex2.approx / rcp.approx): absolute error
-// below 3e-7 on outputs in (0, 1) / (-1, 1), inside the fp32 tolerance of the path (rtol 1e-5).
-__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float gate_tanh(float x) {
-  const float ax = fminf(fabsf(x), 15.f);                  // tanh(15) == 1 in fp32; keeps exp finite
-  const float t = 1.f - __fdividef(2.f, __expf(2.f * ax) + 1.f);
-  return copysignf(t, x);
-}
 
 // exp of a non-positive softmax argument: ex2.approx(x * log2 e).  Relative error <= 2^-22 + |x| 2^-24,
 // i.e. below 1e-6 wherever exp(x) still matters; the weights that dominate the sum have x near 0.
@@ -1260,7 +1252,7 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   // 2 gnn only, 3 head only.  Measured on C3: -2.7 % with one rollout stream, but with the default 4 streams
   // the early-resident blocks hold shared memory the other streams' kernels would have used (+2.9 % with 1,
   // +-0 with 2), so it stays off unless asked for.
-  const char* pdl_env = getenv("DGPPO_PDL");
+  static const char* pdl_env = getenv("DGPPO_PDL");
   const int pdl_mode = pdl_env ? atoi(pdl_env) : 0;
   const bool pdl = pdl_mode == 1 || pdl_mode == 2, pdl_h = pdl_mode == 1 || pdl_mode == 3;
   const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
@@ -1295,9 +1287,14 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   const long total_rows = (long)g.n_graphs * nr;
   const long h_tiles = (total_rows + R - 1) / R;             // CTAs worth of 8-row warp tiles
   const int grid2 = h_tiles < sms ? (int)h_tiles : sms;
-  const char* hv = getenv("DGPPO_HEAD");                    // "wide" (default) | "wr4" | "wr8"
+  // head variant: "tc" (default: tcgen05 3xTF32, head_tc.cu) | "wide" | "wr4" | "wr8" (FFMA kernels, A/B runs)
+  static const char* hv_cached = getenv("DGPPO_HEAD");
+  const char* hv = hv_cached;
+  const size_t hvlen = hv ? strlen(hv) : 0;
+  if (!hv || (hvlen >= 2 && hv[0] == 't' && hv[1] == 'c'))
+    return launch_head_tc(st, P, g, params + L.tc_head, sms, pdl_h);
   const size_t wide_smem = ((size_t)pl.hw_fl + 2 * HID * R3S + 4 * R3S) * sizeof(float);
-  const bool want_wide = !hv || hv[0] == 'w' && hv[1] == 'i';
+  const bool want_wide = hvlen >= 2 && hv[0] == 'w' && hv[1] == 'i';
   if (want_wide && wide_smem <= 227 * 1024) {
     const long w_tiles = (total_rows + R3 - 1) / R3;
     const int grid3 = w_tiles < sms ? (int)w_tiles : sms;      // no more CTAs than full 128-row tiles: spreading a
@@ -1307,8 +1304,7 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
     launch_pdl(pdl_h, head_kernel_wide, grid3, 512, wide_smem, st, P, g, pl, params);
     return (int)cudaGetLastError();
   }
-  const char* wr8 = (hv && hv[2] == '8') ? "1" : "0";
-  if (wr8 && wr8[0] == '1') {
+  if (hvlen >= 3 && hv[2] == '8') {
     err = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.head_smem_bytes);
     if (err != cudaSuccess) return (int)err;
     launch_pdl(pdl_h, head_kernel<8>, grid2, 256, pl.head_smem_bytes, st, P, g, pl, params);

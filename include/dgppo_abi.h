@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DGPPO_ABI_VERSION 4
+#define DGPPO_ABI_VERSION 5
 
 /* negative error codes (positive values are cudaError_t) */
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
@@ -213,7 +213,12 @@ typedef struct DgppoNetCfg {
  *   three are merged at pack time (products in double, rounded once):
  *   out_w [64][4] = ScaleHid.kernel @ [OutputDenseMean.kernel | OutputDenseStdTrans.kernel] (n_out = 2),
  *   out_b [4]     = ScaleHid.bias @ [Mean.kernel | StdTrans.kernel] + [Mean.bias | StdTrans.bias].
- *   value: out_w [64][4] = Dense_0.kernel zero-padded to 4 columns, out_b [4]. */
+ *   value: out_w [64][4] = Dense_0.kernel zero-padded to 4 columns, out_b [4].
+ * tc_head: the B operands of the tensor-core head (tcgen05.mma kind::tf32, 3xTF32 split): for each of
+ *   W = d0w, d1w (K = 64, N = 64), wi, wh (K = 64, N = 192), in that order, a block
+ *   [hi | lo] with hi = TF32(W) (round to nearest), lo = TF32(W - hi), each copy laid out as
+ *   [K/4][N][4]: block[kc][n][j] = W[4 kc + j][n] (the no-swizzle K-major canonical smem layout, so the
+ *   kernel stages it with plain bulk copies).  65536 floats, 16-byte aligned. */
 typedef struct DgppoNetLayout {
   int32_t wqk[2], wagg[2], wu[2], bu[2];
   int32_t wq[2], bq[2], wkt[2];                 /* fallback-kernel blocks, at the tail */
@@ -221,6 +226,7 @@ typedef struct DgppoNetLayout {
   int32_t d0w, d0b, ln0s, ln0b, d1w, d1b, ln1s, ln1b;
   int32_t wi, bi, wh, bhn;
   int32_t out_w, out_b;
+  int32_t tc_head;    /* tensor-core copy of the head / GRU matrices (see above), 65536 floats */
   int32_t total;      /* floats in the packed buffer */
 } DgppoNetLayout;
 
