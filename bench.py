@@ -374,7 +374,7 @@ def run_gpu(args):
                     "ms_per_step": ms_e2e / args.steps},
             # our kernels inside the timed region, per rollout: every env group (stream) launches
             # T x {gnn_layers, head, env_step, [lidar], build_graph}; the reset graph adds [lidar] + build_graph
-            "gpu_launches": args.steps * (algo.rollout_chunks * (5 if lidar else 4) * T + (2 if lidar else 1)),
+            "gpu_launches": args.steps * (algo._n_chunks(b) * (5 if lidar else 4) * T + (2 if lidar else 1)),
             "clocks": clocks,
             "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel_wide", "bound": "hbm",
                          "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -387,7 +387,7 @@ def run_gpu(args):
                          "note": "FP32-FFMA bound kernel reported against HBM as BASELINE's metric asks; "
                                  "see DESIGN.md for the compute roofline"},
             "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof),
-            "rollout_streams": algo.rollout_chunks,
+            "rollout_streams": algo._n_chunks(b),
             "api_collect_with_reset": ({"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT}
                                        if ms_api is not None else {"unavailable": api_err}),
             "rollout_hbm": {"unique_record_bytes_per_env_step": rec_bytes, "achieved_gbs": rollout_gbs,

@@ -82,6 +82,12 @@ SIGNATURES = {
                                       _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dgppo_rollout": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
                                 C.POINTER(DgppoRolloutBuffers), C.c_int32, C.c_int32, _fp]),
+    "dgppo_rollout_graph_create": (_fp, [C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
+                                         C.POINTER(DgppoRolloutBuffers), C.c_int32, C.c_int32,
+                                         C.POINTER(C.c_int32)]),
+    "dgppo_rollout_graph_launch": (C.c_int, [_fp, _fp]),
+    "dgppo_rollout_graph_nodes": (C.c_int, [_fp]),
+    "dgppo_rollout_graph_destroy": (None, [_fp]),
     "dgppo_prof_create": (_fp, [C.c_int32]),
     "dgppo_prof_destroy": (None, [_fp]),
     "dgppo_prof_read": (C.c_int, [_fp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -94,7 +94,8 @@ class DGPPO(Algorithm):
         self.last_prepass: Optional[dict] = None
         self._workspaces: dict = {}
         # independent env groups run on separate streams so env kernels overlap policy kernels
-        self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "4"))
+        # (DGPPO_ROLLOUT_CHUNKS overrides; default by batch size, _n_chunks)
+        self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "0"))
 
     # ------------------------------------------------------------ config / params
     @property
@@ -138,6 +139,13 @@ class DGPPO(Algorithm):
             ent = (tree, torch.from_numpy(P.pack_params(tree, self._cfgs[name])).to(self.device))
             self._packed[name] = ent
         return ent[1]
+
+    def _n_chunks(self, b: int) -> int:
+        """Env groups (streams) of a rollout.  Measured on B200, C3, captured rollouts: 4096 envs - 4 groups
+        best; 512 envs - 1 group 7.4 ms, 2: 8.1, 4: 8.2, 8: 8.6 (kernels too small to share the SMs usefully)."""
+        if self.rollout_chunks > 0:
+            return self.rollout_chunks
+        return 4 if b >= 1024 else 1
 
     # ------------------------------------------------------------------ helpers
     def _cached(self, name: str, key, make):
@@ -217,8 +225,11 @@ class DGPPO(Algorithm):
         b, T = graph0.nodes.shape[0], self._env.max_episode_steps
         if eps is None:
             eps = self._eps_from_key(b_key, (b, T, self.n_agents, self.action_dim))
+        if record is None:       # one stochastic record per shape, reused: the returned Rollout aliases it (see _cached)
+            record = self._cached("record", self._shape_key(b),
+                                  lambda: RolloutRecord(self._env, b, T, graph0.nodes.device, stochastic=True))
         ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
-                                 self.init_rnn_state, record=record, n_chunks=self.rollout_chunks, prof=prof)
+                                 self.init_rnn_state, record=record, n_chunks=self._n_chunks(b), prof=prof)
         if fresh:
             check_reset(self._env)                                  # after the rollout is enqueued
         return ro
@@ -234,7 +245,7 @@ class DGPPO(Algorithm):
                                                         graph0.nodes.device, stochastic=False))
         ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
                                  self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True,
-                                 n_chunks=self.rollout_chunks)
+                                 n_chunks=self._n_chunks(graph0.nodes.shape[0]))
         if fresh:
             check_reset(self._env)
         return ro

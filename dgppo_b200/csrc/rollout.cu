@@ -52,9 +52,23 @@ extern "C" int dgppo_prof_read(void* prof, float* ms_sum4, float* ms_max4) {
   return 0;
 }
 
-extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
-                             const float* params, const DgppoRolloutBuffers* B, int32_t T, int32_t b,
-                             void* prof_) {
+// Resources of the LiDAR look-ahead branch.  Outside a capture they are released as soon as the launches are
+// enqueued (the runtime defers the release until the work has drained); inside a capture they must outlive
+// cudaStreamEndCapture, so the capturing caller passes a holder and releases it afterwards.
+struct AheadRes {
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev;
+  void release() {
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    ev.clear();
+    if (side) cudaStreamDestroy(side);
+    side = nullptr;
+  }
+};
+
+static int rollout_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                        const float* params, const DgppoRolloutBuffers* B, int32_t T, int32_t b,
+                        void* prof_, AheadRes* keep) {
   DgppoProf* prof = (DgppoProf*)prof_;
   if (prof && prof->T != T) return DGPPO_EINVAL;
   auto mark = [&](int t, int k) {
@@ -80,13 +94,20 @@ extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNe
   // Opt-in (DGPPO_LIDAR_AHEAD=1): measured -1.9 % with one rollout stream, but +-0 with the default four
   // env groups (their streams already overlap K2 with other groups' policy kernels) while the cross-stream
   // events triple the host-side submission cost; never under the per-kernel profiler (serial schedule).
-  const char* ahead_env = getenv("DGPPO_LIDAR_AHEAD");
-  const bool ahead = lid && d.n_on > 0 && B->hits_ws2 && !prof && ahead_env && ahead_env[0] == '1';
-  cudaStream_t side_st = nullptr;
-  std::vector<cudaEvent_t> ev;                 // [2 t] state t + 1 ready (main), [2 t + 1] hits t + 2 ready (side)
+  // Inside a captured rollout (keep != nullptr) the branch costs the host nothing - it is a parallel branch of
+  // the graph - and pays when the kernels are too small to fill the GPU (measured, C3, B200: 512 envs 7.37 ->
+  // 6.96 ms, 4 x 256 envs 9.91 -> 9.21 ms; 4 x 1024 envs 28.6 -> 29.3 ms): default on below 1024 envs per
+  // group; DGPPO_LIDAR_AHEAD=0 / 1 forces it.  Launched directly (no graph) it stays opt-in (=1).
+  static const char* ahead_env = getenv("DGPPO_LIDAR_AHEAD");          // read once per process
+  const bool forced_on = ahead_env && ahead_env[0] == '1', forced_off = ahead_env && ahead_env[0] == '0';
+  const bool want_ahead = keep ? (forced_on || (!forced_off && b < 1024)) : forced_on;
+  const bool ahead = lid && d.n_on > 0 && B->hits_ws2 && !prof && want_ahead;
+  AheadRes local_res;
+  AheadRes& res = keep ? *keep : local_res;
+  cudaStream_t& side_st = res.side;
+  std::vector<cudaEvent_t>& ev = res.ev;       // [2 t] state t + 1 ready (main), [2 t + 1] hits t + 2 ready (side)
   auto fail = [&](int rc) {
-    for (auto& e : ev) if (e) cudaEventDestroy(e);
-    if (side_st) cudaStreamDestroy(side_st);
+    if (!keep) res.release();
     return rc;
   };
   if (ahead) {
@@ -153,4 +174,77 @@ extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNe
   fail(0);                                     // events / side stream: released once their work has drained
   if (prof) prof->recorded = true;
   return 0;
+}
+
+extern "C" int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                             const float* params, const DgppoRolloutBuffers* B, int32_t T, int32_t b,
+                             void* prof_) {
+  return rollout_impl(stream, env, net, params, B, T, b, prof_, nullptr);
+}
+
+// ---- captured rollout ---------------------------------------------------------------------------
+// The launch sequence above, recorded ONCE into a CUDA graph and replayed with one launch per rollout:
+// T x (2 policy + step + LiDAR + graph) kernels cost the host 3-4 us each when launched one by one, which
+// is what bounds the rollout once the batch per GPU is small (512 envs per GPU in the 8-GPU configuration).
+// The graph bakes in every pointer of `buf` and `params`: the caller keeps those buffers alive and
+// refills them in place (dgppo_b200/trainer/rollout.py keeps them in the record).
+struct DgppoRolloutGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int n_kernels = 0;
+};
+
+extern "C" void* dgppo_rollout_graph_create(const DgppoEnvCfg* env, const DgppoNetCfg* net, const float* params,
+                                            const DgppoRolloutBuffers* B, int32_t T, int32_t b, int32_t* rc_out) {
+  auto set_rc = [&](int rc) { if (rc_out) *rc_out = rc; };
+  set_rc(DGPPO_EINVAL);
+  if (b < 1) return nullptr;
+  cudaStream_t cs = nullptr;
+  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  DgppoRolloutGraph* G = new DgppoRolloutGraph();
+  cudaError_t err = cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed);
+  AheadRes res;
+  int rc = (err == cudaSuccess) ? rollout_impl(cs, env, net, params, B, T, b, nullptr, &res) : (int)err;
+  cudaGraph_t g = nullptr;
+  if (err == cudaSuccess) {
+    const cudaError_t e2 = cudaStreamEndCapture(cs, &g);      // always end the capture, also after a failed launch
+    if (rc == 0 && e2 != cudaSuccess) rc = (int)e2;
+  }
+  if (rc == 0) {
+    G->graph = g;
+    size_t nn = 0;
+    cudaGraphGetNodes(g, nullptr, &nn);
+    G->n_kernels = (int)nn;
+    err = cudaGraphInstantiate(&G->exec, g, 0);
+    if (err != cudaSuccess) rc = (int)err;
+  }
+  res.release();
+  cudaStreamDestroy(cs);
+  set_rc(rc);
+  if (rc != 0) {
+    if (g) cudaGraphDestroy(g);
+    delete G;
+    cudaGetLastError();
+    return nullptr;
+  }
+  return G;
+}
+
+extern "C" int dgppo_rollout_graph_launch(void* graph, void* stream) {
+  DgppoRolloutGraph* G = (DgppoRolloutGraph*)graph;
+  if (!G || !G->exec) return DGPPO_EINVAL;
+  return (int)cudaGraphLaunch(G->exec, (cudaStream_t)stream);
+}
+
+extern "C" int dgppo_rollout_graph_nodes(void* graph) {
+  DgppoRolloutGraph* G = (DgppoRolloutGraph*)graph;
+  return G ? G->n_kernels : DGPPO_EINVAL;
+}
+
+extern "C" void dgppo_rollout_graph_destroy(void* graph) {
+  DgppoRolloutGraph* G = (DgppoRolloutGraph*)graph;
+  if (!G) return;
+  if (G->exec) cudaGraphExecDestroy(G->exec);
+  if (G->graph) cudaGraphDestroy(G->graph);
+  delete G;
 }

@@ -63,6 +63,35 @@ class RolloutRecord:
         if isinstance(env, LidarEnv) and d.n_obs_nodes > 0:
             self.hits_ws = torch.empty((b, n, env.params["top_k_rays"], 2), **f32)
             self.hits_ws2 = torch.empty_like(self.hits_ws)      # second buffer: LiDAR look-ahead (dgppo_rollout)
+        self._init_graph_state()
+
+    def _init_graph_state(self):
+        # captured-rollout state (dgppo_rollout_graph_*): the graph bakes in device pointers, so the inputs
+        # that change from call to call (eps, goal, obstacles, packed parameters) live in buffers owned here
+        self.graph_inputs: dict = {}
+        self._graph = None
+        self._graph_key = None
+
+    def persistent(self, name: str, src: torch.Tensor) -> torch.Tensor:
+        """Copy `src` into this record's persistent buffer `name` (allocated on first use / shape change)."""
+        buf = self.graph_inputs.get(name)
+        if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+            buf = torch.empty_like(src, memory_format=torch.contiguous_format)
+            self.graph_inputs[name] = buf
+            self._drop_graph()
+        buf.copy_(src)
+        return buf
+
+    def _drop_graph(self):
+        if getattr(self, "_graph", None):
+            _lib.lib().dgppo_rollout_graph_destroy(self._graph)
+        self._graph, self._graph_key = None, None
+
+    def __del__(self):
+        try:
+            self._drop_graph()
+        except Exception:       # interpreter shutdown
+            pass
 
     def nbytes(self) -> int:
         ts = [self.nodes, self.edges, self.states, self.receivers, self.senders, self.node_type,
@@ -84,6 +113,7 @@ class RolloutRecord:
         # the ping-pong state workspace must be contiguous per chunk: give the view its own
         v.agent_ws = torch.empty((2, hi - lo) + tuple(self.agent_ws.shape[2:]), dtype=torch.float32,
                                  device=self.agent_ws.device)
+        v._init_graph_state()
         return v
 
     def graph_view(self, lo: int, hi: int, env_states) -> GraphsTuple:
@@ -135,6 +165,20 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
     if eps is not None:
         eps = eps.contiguous()
         assert eps.shape == (b, T, n, 2) and eps.dtype == torch.float32
+    assert (eps is None) == (rec.log_pis is None), "record built for the other policy mode"
+
+    # Captured rollout (default): one graph launch instead of 5 T kernel launches.  The per-call inputs are
+    # copied into buffers the record owns, whose addresses the graph has baked in.
+    use_graph = prof is None and os.environ.get("DGPPO_GRAPH", "1") != "0"
+    if use_graph:
+        goal = rec.persistent("goal", goal)
+        params_dev = rec.persistent("params", params_dev)
+        if obstacles is not None:
+            obstacles = rec.persistent("obstacles", obstacles)
+        if rays is not None:
+            rays = rec.persistent("rays", rays)
+        if eps is not None:
+            eps = rec.persistent("eps", eps)
 
     buf = _lib.DgppoRolloutBuffers(
         ptr(rec.nodes), ptr(rec.edges), ptr(rec.states), ptr(rec.receivers), ptr(rec.senders),
@@ -142,8 +186,21 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
         ptr(rec.actions), ptr(rec.log_pis) if eps is not None else None, ptr(rec.rewards), ptr(rec.costs),
         ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays), ptr(rec.hits_ws2))
     cfg = env.env_cfg()
-    _lib.check(_lib.lib().dgppo_rollout(stream_ptr(), C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
-                                         C.byref(buf), T, b, prof), "dgppo_rollout")
+    if use_graph:
+        key = (bytes(cfg), bytes(net_cfg), T, b, os.environ.get("DGPPO_HEAD"), os.environ.get("DGPPO_LIDAR_AHEAD"))
+        if rec._graph is None or rec._graph_key != key:
+            rec._drop_graph()
+            rc = C.c_int32(0)
+            # capture on a private stream: wait for the copies above first so nothing of this stream is captured
+            handle = _lib.lib().dgppo_rollout_graph_create(C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
+                                                           C.byref(buf), T, b, C.byref(rc))
+            if not handle:
+                _lib.check(rc.value or -1, "dgppo_rollout_graph_create")
+            rec._graph, rec._graph_key = handle, key
+        _lib.check(_lib.lib().dgppo_rollout_graph_launch(rec._graph, stream_ptr()), "dgppo_rollout_graph_launch")
+    else:
+        _lib.check(_lib.lib().dgppo_rollout(stream_ptr(), C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
+                                             C.byref(buf), T, b, prof), "dgppo_rollout")
 
     sd = d.state_dim
     def env_view(lo, hi):

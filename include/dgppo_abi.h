@@ -333,6 +333,17 @@ int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
                   const float* params, const DgppoRolloutBuffers* buf,
                   int32_t T, int32_t b, void* prof /* nullable */);
 
+/* Captured rollout (the launch-free form of the scan, trainer/utils.py:45-57): the kernel sequence of
+ * dgppo_rollout recorded once into a CUDA graph and replayed with ONE launch per rollout.  The graph bakes
+ * in `params` and every pointer of `buf`: the caller keeps those buffers alive and refills them in place
+ * (initial state into slot 0 / the workspaces, eps, goal, obstacles, packed parameters) before each launch.
+ * create returns NULL on failure with the error in *rc_out (nullable); nodes = kernels in the graph.    */
+void* dgppo_rollout_graph_create(const DgppoEnvCfg* env, const DgppoNetCfg* net, const float* params,
+                                 const DgppoRolloutBuffers* buf, int32_t T, int32_t b, int32_t* rc_out);
+int   dgppo_rollout_graph_launch(void* graph, void* stream);
+int   dgppo_rollout_graph_nodes(void* graph);
+void  dgppo_rollout_graph_destroy(void* graph);
+
 /* Optional per-kernel timing of a rollout (measurement only).  `prof` records
  * cudaEvents on the rollout's stream around the 4 kernels of every step; it
  * never synchronises inside dgppo_rollout.  dgppo_prof_read waits for the last
