@@ -6,12 +6,12 @@ DGPPO <- InforMARLLagr <- InforMARL <- Algorithm
 Constructor arguments, `config`, `params`, `act`, `step`, `collect`,
 `get_Vh`, `update`, `save`, `load` keep the reference's names and meaning.
 Parameters are held as reference-shaped pytrees (NumPy leaves) and as packed
-fp32 device buffers (algo/params.py).  `update` runs the hot-path pre-pass of
-`DGPPO.update` / `update_inner` (deterministic rollout, Vl scan, Vh over all
-(b, T), Dec-OCP GAE, CBF-residual advantage: dgppo.py:136-273) on the GPU and
-returns its products; the PPO minibatch gradient step (dgppo.py:276-321,
-informarl.py:357-457) is the caller's autodiff code and outside this path
-(component 3).
+fp32 device buffers (algo/params.py).  `update` runs the pre-pass of `DGPPO.update` /
+`update_inner` (deterministic rollout, Vl scan, Vh over all (b, T), Dec-OCP
+GAE, CBF-residual advantage: dgppo.py:136-273) on the kernels, then the PPO
+minibatch scan (dgppo.py:276-321, informarl.py:357-457: update_Vl, update_Vh,
+update_policy with gradient clipping and Adam) in `algo/update.py`, whose
+gradients come from torch autograd and are mean-all-reduced over the ranks.
 """
 from __future__ import annotations
 
@@ -26,10 +26,12 @@ import torch
 from .. import _lib
 from ..env.base import MultiAgentEnv, ptr, require_cuda, stream_ptr
 from ..env.envs import check_reset
+from ..trainer import distributed as D
 from ..trainer.data import Rollout
 from ..trainer.rollout import RNN_DIM, RolloutRecord, run_rollout, run_rollout_chunked
 from ..utils.graph import GraphsTuple
 from . import params as P
+from . import update as U
 from .base import Algorithm
 
 
@@ -90,7 +92,10 @@ class DGPPO(Algorithm):
         self._packed: Dict[str, tuple] = {}
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed)
-        self._np_rng = np.random.default_rng(seed)
+        # the deterministic-rollout keys and the minibatch shuffle are per-rank streams (each rank owns its envs)
+        self._np_rng = np.random.default_rng([seed, D.world()[0]])
+        self._train: Dict[str, dict] = {}          # per net: torch leaves + Adam state (algo/update.py)
+        self._lrs = {"policy": lr_actor, "Vl": lr_Vl, "Vh": lr_Vh}
         self.last_prepass: Optional[dict] = None
         self._workspaces: dict = {}
         # independent env groups run on separate streams so env kernels overlap policy kernels
@@ -117,9 +122,15 @@ class DGPPO(Algorithm):
         return {"policy": self._trees["policy"], "Vl": self._trees["Vl"], "Vh": self._trees["Vh"]}
 
     def set_params(self, name: str, tree: dict) -> None:
-        """Replace the pytree of net `name`; its packed device copy is rebuilt on next use."""
+        """Replace the pytree of net `name`; its packed device copy is rebuilt on next use and the training
+        copy takes the new values (the Adam moments are kept, as TrainState.replace(params=...) keeps them)."""
         self._trees[name] = tree
         self._packed.pop(name, None)
+        st = self._train.get(name)
+        if st is not None:
+            with torch.no_grad():
+                for (path, leaf), t in zip(U.tree_leaves(tree), st["leaves"]):
+                    t.copy_(torch.as_tensor(np.asarray(leaf), dtype=t.dtype, device=t.device))
 
     def invalidate(self, name: Optional[str] = None) -> None:
         """Drop the packed device copy of `name` (all nets when None).  Needed only after editing the NumPy
@@ -364,15 +375,25 @@ class DGPPO(Algorithm):
         return A, deriv, acbf, safe.bool()
 
     # -------------------------------------------------------------------- update
-    def update(self, rollout: Rollout, step: int) -> dict:
-        """Hot-path pre-pass of DGPPO.update / update_inner (dgppo.py:136-273).
+    def _train_state(self, name: str) -> dict:
+        st = self._train.get(name)
+        if st is None:
+            tree = U.to_torch_tree(self._trees[name], self.device)
+            leaves = [t for _, t in U.tree_leaves(tree)]
+            st = {"tree": tree, "leaves": leaves, "opt": U.AdamIfFinite(leaves, self._lrs[name])}
+            self._train[name] = st
+        return st
 
-        Runs the deterministic rollout, Vl, Vh (stochastic and deterministic
-        records), both GAE passes and the CBF advantage merge on the GPU.  The
-        tensors the PPO minibatch scan consumes (dgppo.py:276-289) are left in
-        `self.last_prepass`; the gradient step itself is outside this path."""
+    def _sync_params_from_training(self) -> None:
+        """Training leaves -> the NumPy pytrees `params` exposes (and the kernels' packed copies)."""
+        for name, st in self._train.items():
+            self._trees[name] = U.to_numpy_tree(st["tree"])
+            self._packed.pop(name, None)
+
+    def prepass(self, rollout: Rollout, step: int) -> dict:
+        """Everything `update_inner` computes before its minibatch scan (dgppo.py:204-273), on the kernels:
+        deterministic rollout, Vl scan, Vh on both records, both GAE passes, the CBF advantage merge."""
         b = rollout.dones.shape[0]
-        assert rollout.dones.shape[0] * rollout.dones.shape[1] >= self.batch_size
         key = self._np_rng.integers(0, 2 ** 31 - 1, size=b)
         det_rollout = self.det_rollout_fn(self.params, key)
         Vl, Vl_carries = self.scan_Vl(rollout)
@@ -381,17 +402,60 @@ class DGPPO(Algorithm):
         A, deriv, acbf, is_safe = self.cbf_advantage(Ql, Vl, Vh, step)
         Vh_det = self._value_record("Vh", det_rollout, None)
         Qh_det, _ = self.gae(det_rollout.costs, -det_rollout.rewards, Vh_det, Vl)
-        # host-side batching indices exactly as dgppo.py:155-159
-        idx = np.arange(b)
-        self._np_rng.shuffle(idx)
         T = rollout.dones.shape[1]
-        rnn_chunk_ids = np.array(np.array_split(np.arange(T), T // self.rnn_step))
-        batch_idx = np.array(np.array_split(idx, idx.shape[0] // (self.batch_size // T)))
         self.last_prepass = dict(det_rollout=det_rollout, bTp1_Vl=Vl, bT_Vl_rnn_states=Vl_carries[:, :T],
                                  bTp1ah_Vh=Vh, bTah_Qh=Qh, bT_Ql=Ql, bTa_A=A, bTah_cbf_deriv=deriv,
                                  bTah_Acbf=acbf, bTa_is_safe=is_safe, bTp1ah_Vh_det=Vh_det,
-                                 bTah_Qh_det=Qh_det, batch_idx=batch_idx, rnn_chunk_ids=rnn_chunk_ids)
-        return {"eval/safe_data": float(is_safe.float().mean())}
+                                 bTah_Qh_det=Qh_det)
+        return self.last_prepass
+
+    def update(self, rollout: Rollout, step: int) -> dict:
+        """DGPPO.update (dgppo.py:136-170): pre-pass, then `epoch_ppo` passes of the minibatch scan
+        `update_fn` (dgppo.py:276-289): update_Vl -> update_Vh -> update_policy per minibatch."""
+        b, T = rollout.dones.shape
+        rank, world = D.world()
+        mb_envs = (self.batch_size // world) // T        # this rank's share of every minibatch
+        if mb_envs < 1 or b * T * world < self.batch_size:
+            raise ValueError(f"batch_size {self.batch_size} needs at least {self.batch_size // T} environments "
+                             f"in total and T * world_size = {T * world} steps per minibatch; got {b} envs "
+                             f"per rank on {world} rank(s) (dgppo.py:153,159)")
+        if T % self.rnn_step:
+            raise ValueError(f"rnn_step {self.rnn_step} must divide the horizon {T} (dgppo.py:157-158)")
+        pp = self.prepass(rollout, step)
+        det = pp["det_rollout"]
+        gi = U.GraphIndex(self.n_agents, self._env.graph_dims().n_ag, self._env.graph_dims().n_ao,
+                          self._env.graph_dims().n_nodes, self.device)
+        arrays, det_arrays = self._record_arrays(rollout), self._record_arrays(det)
+        n = self.n_agents
+        rnn_det = det.rnn_states.reshape(b, T, n, RNN_DIM)
+        st_pi, st_Vl, st_Vh = self._train_state("policy"), self._train_state("Vl"), self._train_state("Vh")
+        info = {}
+        for _ in range(self.epoch_ppo):
+            idx = np.arange(b)
+            self._np_rng.shuffle(idx)
+            for mb in np.array_split(idx, max(1, b // mb_envs)):
+                ix = torch.as_tensor(mb, dtype=torch.long, device=self.device)
+                g = U.chunk_graphs(arrays, ix, T, gi, torch.float32)
+                loss = U.loss_Vl(st_Vl["tree"], g, pp["bT_Ql"][ix], gi, self.Vl_gnn_layers, self.rnn_step)
+                r = U.clip_and_step(st_Vl["opt"], st_Vl["leaves"], loss, self.max_grad_norm)
+                info.update({"Vl/loss": loss.detach(), "Vl/grad_norm": r["grad_norm"], "Vl/has_nan": r["has_nan"]})
+                gd = U.chunk_graphs(det_arrays, ix, T, gi, torch.float32)
+                loss = U.loss_Vh(st_Vh["tree"], gd, rnn_det[ix], pp["bTah_Qh_det"][ix], gi, self.Vh_gnn_layers)
+                r = U.clip_and_step(st_Vh["opt"], st_Vh["leaves"], loss, self.max_grad_norm)
+                info.update({"Vh/loss_Vh": loss.detach(), "Vh/grad_Vh_norm": r["grad_norm"],
+                             "Vh/grad_Vh_has_nan": r["has_nan"]})
+                eps = torch.randn(rollout.actions[ix].shape, generator=self._gen, device=self.device)
+                loss, pinfo = U.loss_policy(st_pi["tree"], g, rollout.actions[ix], rollout.log_pis[ix],
+                                            pp["bTa_A"][ix], eps, gi, self.actor_gnn_layers, self.rnn_step,
+                                            self.clip_eps, self.coef_ent)
+                r = U.clip_and_step(st_pi["opt"], st_pi["leaves"], loss, self.max_grad_norm)
+                info.update({"policy/loss": loss.detach(), "policy/grad_norm": r["grad_norm"],
+                             "policy/has_nan": r["has_nan"], **pinfo})
+        self._sync_params_from_training()
+        info["policy/log_pi_min"] = rollout.log_pis.min()
+        info["Vl/max_target"], info["Vl/min_target"] = pp["bT_Ql"].max(), pp["bT_Ql"].min()
+        info["eval/safe_data"] = pp["bTa_is_safe"].float().mean()
+        return {k: float(v) for k, v in info.items()}
 
     # ---------------------------------------------------------------- save / load
     def save(self, save_dir: str, step: int):
@@ -408,11 +472,13 @@ class DGPPO(Algorithm):
         for name, fn in (("policy", "actor.pkl"), ("Vl", "Vl.pkl"), ("Vh", "Vh.pkl")):
             with open(os.path.join(path, fn), "rb") as f:
                 tree = pickle.load(f)
-            self._trees[name] = _to_numpy_tree(tree)
-        self._packed.clear()
+            self.set_params(name, _to_numpy_tree(tree))
 
 
 def _to_numpy_tree(t):
-    if isinstance(t, dict):
+    """Any mapping-shaped pytree (dict, flax FrozenDict, ...) with array-like leaves (NumPy, jax) -> nested
+    dicts of fp32 NumPy arrays."""
+    from collections.abc import Mapping
+    if isinstance(t, Mapping):
         return {k: _to_numpy_tree(v) for k, v in t.items()}
     return np.asarray(t, np.float32)

@@ -1,0 +1,302 @@
+"""PPO minibatch update of DGPPO: losses, gradients, clipping, Adam.
+
+Mirrors `DGPPO.update_inner`'s scan body and the three update functions
+(dgppo/algo/dgppo.py:276-321, dgppo/algo/informarl.py:357-457): `update_Vl`
+(chunked BPTT through the centralised value's GRU), `update_Vh` (per-agent
+constraint value, no recurrence: the carry is the stored policy rnn state),
+`update_policy` (chunked BPTT, PPO-clip + entropy), each followed by
+`compute_norm_and_clip` (trainer/utils.py:113-118) and `optax.adam` wrapped in
+`apply_if_finite` (informarl.py:131-132, dgppo.py:310-311).
+
+The reference obtains the gradients from jax.grad; here the same forward
+functions are written over torch tensors and differentiated by torch autograd
+(library arithmetic on the GPU: this is the one part of the training step that
+is NOT hand-written CUDA; the forward used for ROLLOUTS stays the kernels).
+The GraphTransformer is evaluated in the kernels' regrouped form - receivers
+are agents only and masked slots (recv = send = pad) feed nothing an agent reads
+ - so activations are (graphs, agents, slots) instead of
+(graphs, edges, heads, width).
+
+Data parallel: every rank holds `b / world` environments and an equal share
+of each minibatch; the flat gradient of each net is mean-all-reduced (NCCL)
+before clipping, which reproduces the single-device mean.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..trainer import distributed as D
+
+N_HEADS = 3
+STD_DEV_INIT_INV = float(np.log(np.exp(0.5) - 1.0))       # policy.py:54-59
+STD_DEV_MIN = 1e-5
+
+
+# ----------------------------------------------------------------- pytrees
+def tree_leaves(tree, prefix=()) -> List[Tuple[tuple, object]]:
+    """(path, leaf) pairs in sorted-key order (jax's dict flattening order)."""
+    if isinstance(tree, dict):
+        out = []
+        for k in sorted(tree):
+            out += tree_leaves(tree[k], prefix + (k,))
+        return out
+    return [(prefix, tree)]
+
+
+def tree_map(fn, tree):
+    if isinstance(tree, dict):
+        return {k: tree_map(fn, v) for k, v in tree.items()}
+    return fn(tree)
+
+
+def to_torch_tree(tree, device, dtype=torch.float32, requires_grad=True):
+    return tree_map(lambda a: torch.tensor(np.asarray(a), device=device, dtype=dtype, requires_grad=requires_grad), tree)
+
+
+def to_numpy_tree(tree):
+    return tree_map(lambda t: t.detach().to(torch.float32).cpu().numpy(), tree)
+
+
+# ------------------------------------------------------------------ layers
+def dense(x, p):
+    y = x @ p["kernel"]
+    return y + p["bias"] if "bias" in p else y
+
+
+def layer_norm(x, p, eps=1e-6):
+    """flax nn.LayerNorm defaults (fast variance, clipped at 0)."""
+    mean = x.mean(-1, keepdim=True)
+    mean2 = (x * x).mean(-1, keepdim=True)
+    var = torch.clamp(mean2 - mean * mean, min=0.0)
+    return (x - mean) * (torch.rsqrt(var + eps) * p["scale"]) + p["bias"]
+
+
+def mlp_head(x, p):
+    for i in range(2):
+        x = torch.relu(layer_norm(dense(x, p[f"Dense_{i}"]), p[f"LayerNorm_{i}"]))
+    return x
+
+
+def gru_cell(p_rnn, h, x):
+    (c,) = list(p_rnn.values())
+    r = torch.sigmoid(dense(x, c["ir"]) + dense(h, c["hr"]))
+    z = torch.sigmoid(dense(x, c["iz"]) + dense(h, c["hz"]))
+    n = torch.tanh(dense(x, c["in"]) + r * dense(h, c["hn"]))
+    return (1.0 - z) * n + z * h
+
+
+class GraphIndex:
+    """Static slot structure of an env's graphs: receiver agent i owns `deg` edge slots (agents, goals,
+    obstacles / hits); slot (i, t) is edge `eidx[i, t]` of the flat edge list (utils/graph.py:212-247)."""
+
+    def __init__(self, n: int, n_ag: int, n_ao: int, n_nodes: int, device):
+        self.n, self.N, self.deg = n, n_nodes, n + n_ag + n_ao
+        i = np.arange(n)[:, None]
+        e = np.concatenate([i * n + np.arange(n)[None], n * n + i * n_ag + np.arange(n_ag)[None],
+                            n * n + n * n_ag + i * n_ao + np.arange(n_ao)[None]], axis=1)
+        self.eidx = torch.as_tensor(e.reshape(-1), dtype=torch.long, device=device)     # (n * deg)
+
+
+def graph_transformer(p, x, edge_feat, sidx, mask, gi: GraphIndex, d: int, agents_only: bool):
+    """One GraphTransformer layer + update (nn/gnn.py:78-117) in receiver-major form.
+    x (B,N,in); edge_feat (B,n,deg,4); sidx (B,n,deg) sender node of each slot; mask (B,n,deg) slot is live."""
+    B, N, n, H = x.shape[0], gi.N, gi.n, N_HEADS
+    q = dense(x[:, :n], p["Dense_0"]).reshape(B, n, H, d)
+    k = dense(x, p["Dense_1"]).reshape(B, N, H, d)
+    v = dense(x, p["Dense_2"]).reshape(B, N, H, d)
+    scores = torch.einsum("bihd,bjhd->bhij", q, k) / math.sqrt(d)                        # (B,H,n,N)
+    sx = sidx.unsqueeze(1).expand(B, H, n, gi.deg)
+    s = torch.gather(scores, 3, sx)
+    m = mask.unsqueeze(1)
+    s = s.masked_fill(~m, -torch.inf)
+    smax = s.amax(dim=-1, keepdim=True)
+    smax = torch.where(torch.isfinite(smax), smax, torch.zeros_like(smax))              # rows without a live slot
+    ex = torch.exp(s - smax) * m
+    a = ex / ex.sum(-1, keepdim=True).clamp_min(1e-38)                                   # segment_softmax per head
+    a_full = torch.zeros((B, H, n, N), dtype=x.dtype, device=x.device).scatter_add(3, sx, a)
+    agg_v = torch.einsum("bhij,bjhd->bihd", a_full, v)                                   # sum_e a (W_v x_s + b_v)
+    ae = torch.einsum("bhit,bitc->bihc", a, edge_feat)                                   # sum_e a edge_e
+    we = p["Dense_3"]["kernel"].reshape(-1, H, d)                                        # (4, H, d)
+    agg_e = torch.einsum("bihc,chd->bihd", ae, we)
+    agg = (agg_v + agg_e).mean(dim=2)                                                    # mean over heads
+    upd = dense(x[:, :n] if agents_only else x, p["Dense_4"])
+    if agents_only:
+        return torch.relu(upd + agg)
+    return torch.relu(torch.cat([upd[:, :n] + agg, upd[:, n:]], dim=1))
+
+
+def gnn(p, g, gi: GraphIndex, n_layers: int, msg_dim=32, out_dim=64):
+    """GraphTransformerGNN (nn/gnn.py:127-142) -> agent embeddings (B,n,64)."""
+    x = g["nodes"]
+    for i in range(n_layers):
+        last = i == n_layers - 1
+        x = graph_transformer(p[f"GraphTransformer_{i}"], x, g["edge_feat"], g["sidx"], g["mask"], gi,
+                              out_dim if last else msg_dim, agents_only=last)
+    return x
+
+
+def prep_graphs(nodes, edges, recv, send, gi: GraphIndex, dtype):
+    """Flat graph arrays (B,N,nd), (B,E,4), (B,E), (B,E) -> the receiver-major inputs of `gnn`."""
+    B = nodes.shape[0]
+    pad = gi.N - 1
+    r = recv[:, gi.eidx].reshape(B, gi.n, gi.deg)
+    s = send[:, gi.eidx].reshape(B, gi.n, gi.deg).long()
+    mask = r != pad
+    return {"nodes": nodes.to(dtype), "edge_feat": edges[:, gi.eidx].reshape(B, gi.n, gi.deg, -1).to(dtype),
+            "sidx": torch.where(mask, s, torch.zeros_like(s)), "mask": mask}
+
+
+# ------------------------------------------------------------- tanh-Normal
+def _normal_log_prob(x, loc, scale):
+    dd = x / scale - loc / scale
+    return -0.5 * dd * dd - (0.5 * math.log(2.0 * math.pi) + torch.log(scale))
+
+
+def tanh_normal_log_prob(value, loc, scale, threshold=0.999):
+    """TanhTransformedDistribution.log_prob, summed over the action axis (distribution.py:25-35)."""
+    inv_thr = math.atanh(threshold)
+    log_eps = math.log(1.0 - threshold)
+    lp_left = torch.special.log_ndtr((-inv_thr - loc) / scale) - log_eps
+    lp_right = torch.special.log_ndtr(-((inv_thr - loc) / scale)) - log_eps
+    v = torch.clamp(value, -threshold, threshold)
+    x = torch.atanh(v)
+    fldj = 2.0 * (math.log(2.0) - x - torch.nn.functional.softplus(-2.0 * x))
+    inner = _normal_log_prob(x, loc, scale) - fldj
+    lp = torch.where(v <= -threshold, lp_left, torch.where(v >= threshold, lp_right, inner))
+    return lp.sum(-1)
+
+
+def tanh_normal_entropy(loc, scale, eps):
+    """TanhTransformedDistribution.entropy (distribution.py:37-43): Normal entropy + the Tanh forward
+    log-det-Jacobian at ONE reparameterised sample, summed over the action axis."""
+    z = loc + scale * eps
+    fldj = 2.0 * (math.log(2.0) - z - torch.nn.functional.softplus(-2.0 * z))
+    ent = 0.5 + 0.5 * math.log(2.0 * math.pi) + torch.log(scale)
+    return (ent + fldj).sum(-1)
+
+
+# ---------------------------------------------------------------- networks
+def policy_step(params, emb, h):
+    """Head + GRU + TanhNormal parameters for agent embeddings emb (B,n,64), carry h (B,n,64)."""
+    p = params["params"]
+    base = p["PolicyNet_0"]
+    x = mlp_head(emb, base["PolicyGNNHead"])
+    h = gru_cell(base["RNN_0"], h, x)
+    f = dense(h, p["ScaleHid"])
+    mean = dense(f, p["OutputDenseMean"])
+    std = torch.nn.functional.softplus(dense(f, p["OutputDenseStdTrans"]) + STD_DEV_INIT_INV) + STD_DEV_MIN
+    return mean, std, h
+
+
+def value_step(params, emb, h):
+    p = params["params"]
+    x = mlp_head(emb, p["ValueGNNHead"])
+    h = gru_cell(p["RNN_0"], h, x)
+    return dense(h, p["Dense_0"]), h
+
+
+# ------------------------------------------------------------------ losses
+def chunk_graphs(rollout_arrays, idx, T, gi, dtype):
+    """Graphs of envs `idx`, all T slots, flattened env-major: (mb*T, ...)."""
+    nodes, edges, recv, send = (a[idx, :T] for a in rollout_arrays)
+    mb = nodes.shape[0]
+    return prep_graphs(nodes.reshape((mb * T,) + nodes.shape[2:]), edges.reshape((mb * T,) + edges.shape[2:]),
+                       recv.reshape(mb * T, -1), send.reshape(mb * T, -1), gi, dtype)
+
+
+def loss_Vl(params, g, targets, gi, n_layers, rnn_step):
+    """update_Vl.get_loss_ (informarl.py:367-374): scan_Vl over chunks of rnn_step slots, zero initial carry.
+    g: graphs (mb*T, ...); targets (mb, T)."""
+    mb, T = targets.shape
+    emb = gnn(params["params"]["GraphTransformerGNN_0"], g, gi, n_layers).mean(dim=1)       # (mb*T, 64)
+    emb = emb.reshape(mb, T // rnn_step, rnn_step, -1)
+    h = torch.zeros((mb, T // rnn_step, emb.shape[-1]), dtype=emb.dtype, device=emb.device)
+    out = []
+    for t in range(rnn_step):
+        v, h = value_step(params, emb[:, :, t], h)
+        out.append(v[..., 0])
+    Vl = torch.stack(out, dim=2).reshape(mb, T)
+    return (0.5 * (Vl - targets) ** 2).mean()
+
+
+def loss_Vh(params, g, rnn_states, targets, gi, n_layers):
+    """update_Vh.get_loss (dgppo.py:304-311): no recurrence, the carry is the stored rnn state.
+    rnn_states (mb, T, n, 64); targets (mb, T, n, n_cost)."""
+    mb, T, n, _ = rnn_states.shape
+    emb = gnn(params["params"]["GraphTransformerGNN_0"], g, gi, n_layers)                   # (mb*T, n, 64)
+    Vh, _ = value_step(params, emb, rnn_states.reshape(mb * T, n, -1))
+    return (0.5 * (Vh.reshape(targets.shape) - targets) ** 2).mean()
+
+
+def loss_policy(params, g, actions, log_pis_old, adv, eps, gi, n_layers, rnn_step, clip_eps, coef_ent):
+    """update_policy.get_loss_ (informarl.py:416-437).  actions (mb,T,n,2), log_pis_old / adv (mb,T,n),
+    eps (mb,T,n,2) the N(0,1) draw behind the one-sample entropy estimate."""
+    mb, T, n, nu = actions.shape
+    C = T // rnn_step
+    emb = gnn(params["params"]["PolicyNet_0"]["GraphTransformerGNN_0"], g, gi, n_layers)    # (mb*T, n, 64)
+    emb = emb.reshape(mb, C, rnn_step, n, -1)
+    act = actions.reshape(mb, C, rnn_step, n, nu)
+    ep = eps.reshape(mb, C, rnn_step, n, nu)
+    h = torch.zeros((mb, C, n, emb.shape[-1]), dtype=emb.dtype, device=emb.device)
+    lps, ents = [], []
+    for t in range(rnn_step):
+        mean, std, h = policy_step(params, emb[:, :, t], h)
+        lps.append(tanh_normal_log_prob(act[:, :, t], mean, std))
+        ents.append(tanh_normal_entropy(mean, std, ep[:, :, t]))
+    log_pis = torch.stack(lps, dim=2).reshape(mb, T, n)
+    entropy = torch.stack(ents, dim=2).reshape(mb, T, n)
+    ratio = torch.exp(log_pis - log_pis_old)
+    l1 = -ratio * adv
+    l2 = -torch.clamp(ratio, 1.0 - clip_eps, 1.0 + clip_eps) * adv
+    loss = torch.maximum(l1, l2).mean() - coef_ent * entropy.mean()
+    info = {"policy/clip_frac": (l2 > l1).float().mean(), "policy/entropy": entropy.mean(),
+            "policy/total_variation_dist": 0.5 * (ratio - 1.0).abs().mean()}
+    return loss, info
+
+
+# --------------------------------------------------------------- optimiser
+class AdamIfFinite:
+    """optax.apply_if_finite(optax.adam(lr), max_consecutive_errors) on a list of leaves
+    (b1 0.9, b2 0.999, eps 1e-8): a step with any non-finite gradient is skipped."""
+
+    def __init__(self, leaves: List[torch.Tensor], lr: float, b1=0.9, b2=0.999, eps=1e-8):
+        self.leaves, self.lr, self.b1, self.b2, self.eps = leaves, lr, b1, b2, eps
+        self.m = [torch.zeros_like(p) for p in leaves]
+        self.v = [torch.zeros_like(p) for p in leaves]
+        self.count = 0
+        self.notfinite_count = 0
+
+    @torch.no_grad()
+    def step(self, grads: List[torch.Tensor], finite: bool):
+        if not finite:
+            self.notfinite_count += 1
+            return
+        self.count += 1
+        c1, c2 = 1.0 - self.b1 ** self.count, 1.0 - self.b2 ** self.count
+        torch._foreach_mul_(self.m, self.b1)
+        torch._foreach_add_(self.m, grads, alpha=1.0 - self.b1)
+        torch._foreach_mul_(self.v, self.b2)
+        torch._foreach_addcmul_(self.v, grads, grads, value=1.0 - self.b2)
+        denom = torch._foreach_sqrt(self.v)
+        torch._foreach_div_(denom, math.sqrt(c2))
+        torch._foreach_add_(denom, self.eps)
+        torch._foreach_addcdiv_(self.leaves, self.m, denom, value=-self.lr / c1)
+
+
+def clip_and_step(opt: AdamIfFinite, leaves: List[torch.Tensor], loss: torch.Tensor, max_norm: float) -> dict:
+    """grad -> mean all-reduce over ranks (one flat buffer) -> has_any_nan_or_inf -> compute_norm_and_clip
+    (trainer/utils.py:113-118: g / max(max_norm, |g|) * max_norm) -> Adam."""
+    grads = list(torch.autograd.grad(loss, leaves))
+    grads = D.allreduce_mean_flat(grads)
+    with torch.no_grad():
+        sq = torch.stack([(g * g).sum() for g in grads]).sum()
+        g_norm = torch.sqrt(sq)
+        finite = bool(torch.isfinite(sq))
+        scale = max_norm / torch.clamp(g_norm, min=max_norm)
+        grads = [g * scale for g in grads]
+    opt.step(grads, finite)
+    return {"grad_norm": g_norm, "has_nan": 0.0 if finite else 1.0}

@@ -31,8 +31,17 @@ class Trainer:
         self.model_dir = os.path.join(log_dir, "models")
         if self.save_log:
             os.makedirs(self.model_dir, exist_ok=True)
-        self.rng = np.random.default_rng(seed)
+        self.rng = np.random.default_rng(seed)       # the same stream on every rank: keys are drawn globally, then sharded
         self.update_steps = 0
+        rank, world = D.world()
+        if n_env_train % world:
+            raise ValueError(f"n_env_train = {n_env_train} must be a multiple of the number of ranks ({world}): the "
+                             "gradient mean over ranks equals the single-device mean only for equal shards")
+        T = env.max_episode_steps
+        bs = getattr(algo, "batch_size", None)
+        if bs is not None and (bs % (world * T) or (n_env_train // world) * T * world < bs):
+            raise ValueError(f"batch_size = {bs} must be a multiple of world_size * T = {world * T} and at most "
+                             f"n_env_train * T = {n_env_train * T} (dgppo.py:153-159)")
 
     def evaluate(self, step: int, start_time: float) -> dict:
         """trainer.py:105-125: deterministic rollouts on n_env_test fixed keys."""
@@ -69,5 +78,8 @@ class Trainer:
             keys = self.rng.integers(0, 2 ** 31 - 1, size=self.n_env_train)
             rollouts = self.algo.collect(self.algo.params, D.shard_keys(keys))
             # update the algorithm (trainer.py:137)
-            self.algo.update(rollouts, step)
+            update_info = self.algo.update(rollouts, step)
             self.update_steps += 1
+            if D.world()[0] == 0 and step % self.eval_interval == 0 and update_info:
+                keys_ = ("policy/loss", "Vl/loss", "Vh/loss_Vh", "policy/entropy", "eval/safe_data")
+                print("        " + ", ".join(f"{k}: {update_info[k]:.4g}" for k in keys_ if k in update_info))

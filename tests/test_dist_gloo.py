@@ -45,6 +45,66 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _update_worker(rank, world, port, out):
+    """Each rank takes half of a minibatch: after the flat mean all-reduce inside clip_and_step both ranks
+    must hold the parameters a single process gets from the whole minibatch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dgppo_b200.algo import params as P
+        from dgppo_b200.algo import update as U
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from test_update_cpu import make_graph, torch_graph
+        rng = np.random.default_rng(7)
+        mb, T = 4, 2
+        gr, dims = make_graph(rng, mb * T)
+        n = dims[0]
+        hs = rng.standard_normal((mb, T, n, 64)) * 0.3
+        tgt = rng.standard_normal((mb, T, n, 2))
+        vh = P.init_value_params(7, 4, 2, 1, seed=6, jitter=0.1)
+
+        def run(rows, distributed):
+            sel = {k: v.reshape((mb, T) + v.shape[1:])[rows].reshape((len(rows) * T,) + v.shape[1:]) for k, v in gr.items()}
+            tg, gi = torch_graph(sel, dims, torch.float64)
+            tree = U.to_torch_tree(vh, "cpu", torch.float64)
+            leaves = [t for _, t in U.tree_leaves(tree)]
+            opt = U.AdamIfFinite(leaves, 1e-3)
+            loss = U.loss_Vh(tree, tg, torch.tensor(hs[rows]), torch.tensor(tgt[rows]), gi, 1)
+            if distributed:
+                U.clip_and_step(opt, leaves, loss, 2.0)
+            else:       # single process: same code path with the collective switched off
+                saved = U.D.allreduce_mean_flat
+                U.D.allreduce_mean_flat = lambda g: list(g)
+                try:
+                    U.clip_and_step(opt, leaves, loss, 2.0)
+                finally:
+                    U.D.allreduce_mean_flat = saved
+            return torch.cat([t.detach().reshape(-1) for t in leaves])
+        mine = run(list(range(rank * mb // world, (rank + 1) * mb // world)), True)
+        full = run(list(range(mb)), False)
+        assert torch.allclose(mine, full, rtol=1e-9, atol=1e-12), float((mine - full).abs().max())
+        out.put((rank, "ok"))
+    except Exception as e:          # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_update_equals_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_update_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    assert res == {0: "ok", 1: "ok"}, res
+
+
 def test_two_rank_gloo():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")

@@ -1,0 +1,78 @@
+"""DGPPO.update end to end on the GPU: the torch forward of algo/update.py against the CUDA kernels' outputs
+stored in the rollout, and one full update step (parameters move, losses finite, kernels pick the new weights up)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n_env=32, T=32, batch=1024):
+    from dgppo_b200.algo import make_algo
+    from dgppo_b200.env import make_env
+    env = make_env("LidarSpread", num_agents=3, num_obs=3, max_step=T)
+    algo = make_algo("dgppo", env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
+                     action_dim=env.action_dim, n_agents=env.num_agents, batch_size=batch, rnn_step=16, seed=3)
+    return env, algo
+
+
+def test_torch_forward_matches_kernels_on_rollout():
+    """Chunk 0 of the BPTT starts from the zero carry the rollout started from, so for t < rnn_step the
+    recomputed log_pi must equal the kernels' (ratio == 1 before the first update), and Vh likewise."""
+    from dgppo_b200.algo import update as U
+    env, algo = _setup()
+    ro = algo.collect(algo.params, np.arange(32) + 11)
+    b, T = ro.rewards.shape
+    n = env.num_agents
+    d = env.graph_dims()
+    gi = U.GraphIndex(n, d.n_ag, d.n_ao, d.n_nodes, algo.device)
+    arrays = algo._record_arrays(ro)
+    ix = torch.arange(b, device=algo.device)
+    g = U.chunk_graphs(arrays, ix, T, gi, torch.float32)
+    tree = U.to_torch_tree(algo.params["policy"], algo.device, requires_grad=False)
+    emb = U.gnn(tree["params"]["PolicyNet_0"]["GraphTransformerGNN_0"], g, gi, 2).reshape(b, T, n, -1)
+    h = torch.zeros((b, n, 64), device=algo.device)
+    for t in range(16):
+        mean, std, h = U.policy_step(tree, emb[:, t], h)
+        lp = U.tanh_normal_log_prob(ro.actions[:, t], mean, std)
+        torch.testing.assert_close(lp, ro.log_pis[:, t], rtol=2e-4, atol=2e-4)
+        if t + 1 < T:       # the carry the kernels stored for the next step
+            torch.testing.assert_close(h, ro.rnn_states[:, t + 1].reshape(b, n, 64), rtol=1e-4, atol=1e-5)
+    # Vh over the record vs the torch value net
+    Vh = algo._value_record("Vh", ro, None)
+    tv = U.to_torch_tree(algo.params["Vh"], algo.device, requires_grad=False)
+    embv = U.gnn(tv["params"]["GraphTransformerGNN_0"], g, gi, 1)
+    out, _ = U.value_step(tv, embv, ro.rnn_states.reshape(b * T, n, 64))
+    torch.testing.assert_close(out.reshape(b, T, n, -1), Vh[:, :T], rtol=1e-4, atol=1e-5)
+
+
+def test_update_step_moves_parameters_and_kernels_follow():
+    env, algo = _setup()
+    keys = np.arange(32) + 5
+    ro = algo.collect(algo.params, keys)
+    before = {k: np.concatenate([np.ravel(v) for _, v in __import__("dgppo_b200.algo.update", fromlist=["x"]).tree_leaves(t)])
+              for k, t in algo.params.items()}
+    a0 = ro.actions.clone()
+    info = algo.update(ro, 0)
+    for k in ("policy/loss", "Vl/loss", "Vh/loss_Vh", "policy/grad_norm", "Vl/grad_norm", "Vh/grad_Vh_norm",
+              "policy/entropy", "policy/clip_frac", "eval/safe_data"):
+        assert k in info and np.isfinite(info[k]), (k, info.get(k))
+    assert info["policy/has_nan"] == 0.0 and info["policy/clip_frac"] <= 1.0
+    from dgppo_b200.algo import update as U
+    for k, t in algo.params.items():
+        after = np.concatenate([np.ravel(v) for _, v in U.tree_leaves(t)])
+        delta = np.abs(after - before[k]).max()
+        assert 0 < delta < 0.05, (k, delta)                    # Adam: |step| <= lr per parameter and update
+    # the kernels run with the updated weights: same keys and noise, different actions
+    ro2 = algo.collect(algo.params, keys)
+    assert not torch.equal(ro2.actions, a0)
+    # a second update reuses the optimiser state (count advances)
+    algo.update(ro2, 1)
+    assert algo._train["policy"]["opt"].count == 2 * algo.epoch_ppo * max(1, 32 // (1024 // 32))
+
+
+def test_update_rejects_inconsistent_sizes():
+    env, algo = _setup(batch=1024 * 64)
+    ro = algo.collect(algo.params, np.arange(32))
+    with pytest.raises(ValueError):
+        algo.update(ro, 0)
