@@ -5,12 +5,15 @@
     python bench.py --impl reference --steps K --warmup W  # CPU arm (oracle port)
 
 One "step" is one full rollout (algo.collect: T = 128 env steps) of the
-workload's environments on each rank: BASELINE.json configs[2], LidarSpread
-n=8 obs=8 32 rays, 4096 envs per GPU ("scaling": "weak"; envs are independent,
-no data-path collective).  `value` = agent-steps of all ranks / max-over-ranks
-device time, inputs resident in HBM; `e2e` = the same through algo.collect from
-pinned HOST state buffers with the H2D copy of the initial states and the D2H
-read of rewards+costs inside the timed region.  Prints ONE JSON line on rank 0.
+workload's environments: BASELINE.json configs[2], LidarSpread n=8 obs=8 32
+rays, 4096 envs IN TOTAL, sharded over the ranks ("scaling": "strong": 4096 /
+N envs per GPU - the curve BASELINE.json names; envs are independent, no
+data-path collective).  `--scaling weak` keeps 4096 envs per GPU instead; for
+N > 1 the default run measures that too and reports it under "weak_scaling".
+`value` = agent-steps of all ranks / max-over-ranks device time, inputs
+resident in HBM; `e2e` = the same through algo.collect from pinned HOST state
+buffers with the H2D copy of the initial states and the D2H read of
+rewards+costs inside the timed region.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -74,33 +77,30 @@ def _cpu_shard(job):
     return time.perf_counter() - t0
 
 
-def cpu_rollout_rate(w, target_s=12.0, seed=0):
+CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS = 16, 32     # per worker process: a FIXED, stated sample (not grown to a time budget)
+
+
+def cpu_rollout_rate(w, seed=0, rounds=1):
     """Time the oracle port (NumPy restatement of the reference rollout) on ALL host cores: one worker
-    process per core, each rolling out its own shard of environments (the same data parallelism the
-    reference's vmap exposes), on a bounded sample of the workload grown until a round takes
-    ~target_s.  -> agent-steps/s (all workers, wall clock), sample description, workers."""
+    process per core, each rolling out its own shard of CPU_SAMPLE_ENVS environments for CPU_SAMPLE_STEPS
+    steps (the same data parallelism the reference's vmap exposes).  The rate is per agent-step, so the
+    full workload's time is an EXTRAPOLATION from this sample.  -> agent-steps/s, sample description, workers."""
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
     workers = max(1, min(os.cpu_count() or 1, 64))      # one process per core; capped so start-up stays short
     n = w["n"]
-    b, T = 8, 4
-    rate, sample = 0.0, ""
+    b, T = CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS
+    if w["n"] >= 64:
+        b, T = 2, 8                                      # C5 graphs are 60x larger
     with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as pool:
         list(pool.map(_cpu_shard, [(w, 2, 1, 0)] * workers))            # start the workers, import numpy
-        while True:
-            jobs = [(w, b, T, seed * 1000 + i) for i in range(workers)]
-            t0 = time.perf_counter()
-            list(pool.map(_cpu_shard, jobs))
-            dt = time.perf_counter() - t0
-            rate = workers * b * T * n / dt
-            sample = (f"{workers} processes x {b} envs x {T} steps of {w['env']} n={n} obs={w['obs']} "
-                      f"({dt:.1f} s wall)")
-            if dt >= target_s * 0.5 or b * T >= 64 * 32:
-                break
-            grow = min(8.0, max(2.0, target_s / max(dt, 1e-3)))
-            if T < 32:
-                T = int(min(32, T * 2)); grow /= 2
-            b = int(min(64, max(b + 1, b * grow)))
+        t0 = time.perf_counter()
+        for r in range(rounds):
+            list(pool.map(_cpu_shard, [(w, b, T, seed * 1000 + r * 100 + i) for i in range(workers)]))
+        dt = time.perf_counter() - t0
+    rate = rounds * workers * b * T * n / dt
+    sample = (f"{rounds} round(s) of {workers} processes x {b} envs x {T} steps of {w['env']} n={n} obs={w['obs']} "
+              f"({dt:.1f} s wall); extrapolated per agent-step to the full workload")
     return rate, sample, workers
 
 
@@ -113,7 +113,7 @@ def run_reference(args):
     vals = []
     sample = ""
     for i in range(args.warmup + args.steps):
-        rate, sample, cores = cpu_rollout_rate(w, target_s=max(4.0, min(20.0, 60.0 / max(1, args.steps))), seed=i)
+        rate, sample, cores = cpu_rollout_rate(w, seed=i)
         if i >= args.warmup:
             vals.append(rate)
     v = float(np.mean(vals))
@@ -121,9 +121,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['env']} n={w['n']} obs={w['obs']} 32 rays, "
-                               f"{w['envs']} envs/GPU x T={T_STEPS}", "note": "CPU arm runs a bounded sample"},
+                               f"{w['envs']} envs in total x T={T_STEPS}",
+                   "note": "CPU arm: each step times a fixed bounded sample; value and ms_per_step are EXTRAPOLATED "
+                           "from it per agent-step (the full workload was not run on the CPU)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "what": "NumPy restatement of the reference rollout (jax is not installable in this image)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,10 +185,6 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from dgppo_b200 import _lib
-    from dgppo_b200.algo import make_algo
-    from dgppo_b200.env import make_env
-    from dgppo_b200.env.envs import LidarEnvState, MPEEnvState, Rectangle, rect_record
-    from dgppo_b200.trainer.rollout import RolloutRecord
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,14 +194,51 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
-    b = args.envs or w["envs"]
-    if args.scaling == "strong":
-        b = b // world
+    total = args.envs or w["envs"]
+    b = total // world if args.scaling == "strong" else total
+    m = measure(args, w, b, world, rank, local, full=True)
+    weak = None
+    if world > 1 and args.scaling == "strong":        # the weak curve beside the named (strong) one
+        weak = measure(args, w, total, world, rank, local, full=False)
+    if rank == 0:
+        line = m["line"]
+        if weak is not None:
+            line["weak_scaling"] = {"value": weak["value"], "unit": UNIT, "ms_per_step": weak["ms_per_step"],
+                                    "envs_per_gpu": total, "e2e": weak["e2e"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def traffic_record(workload, b):
+    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this build
+    (profiles/traffic.json, written by tools/ncu_traffic.py together with the commit it was taken at)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        rec = json.load(f)
+    if rec.get("workload") != workload or rec.get("envs") != b:
+        return None
+    return rec
+
+
+def measure(args, w, b, world, rank, local, full):
+    import torch
+    import torch.distributed as dist
+    from dgppo_b200 import _lib
+    from dgppo_b200.algo import make_algo
+    from dgppo_b200.env import make_env
+    from dgppo_b200.env.envs import LidarEnvState, MPEEnvState, Rectangle, rect_record
+    from dgppo_b200.trainer.rollout import RolloutRecord
+
+    dev = torch.device("cuda", local)
     n, T = w["n"], T_STEPS
 
     env = make_env(w["env"], num_agents=n, num_obs=w["obs"], max_step=T)
+    # the update's minibatch: the reference default 16384 steps = 128 envs x T, split evenly over the ranks
     algo = make_algo("dgppo", env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
-                     action_dim=env.action_dim, n_agents=n, batch_size=min(16384, b * T), seed=rank)
+                     action_dim=env.action_dim, n_agents=n, batch_size=min(16384, b * T * world), seed=rank)
     d = env.graph_dims()
 
     # synthetic reset states (SURVEY.md 8d), one independent shard per rank, in PINNED host memory
@@ -251,7 +286,7 @@ def run_gpu(args):
         """Hot path with inputs already in HBM: noise draw + reset graph + T-step rollout."""
         g0 = reset_graph(agent_d, goal_d, obs_d)
         eps = torch.randn((b, T, n, 2), device=dev, dtype=torch.float32)
-        if use_prof:      # per-kernel event timing: one stream, no overlap between env groups
+        if use_prof:      # per-kernel event timing: one stream, no graph, no overlap between env groups
             chunks, algo.rollout_chunks = algo.rollout_chunks, 1
             try:
                 return algo.collect(algo.params, None, eps=eps, graph0=g0, record=record, prof=prof)
@@ -294,6 +329,17 @@ def run_gpu(args):
     sampler.start()
     ms = timed(lambda: step_resident(False), args.steps)
     clocks = sampler.stop()
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    units = b * T * n * world
+    value = units * args.steps / (ms * 1e-3)
+    e2e = {"value": units * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
+    if not full:
+        _lib.lib().dgppo_prof_destroy(prof)
+        return {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e}
+
     # per-kernel device time: the same rollout once more on ONE stream with CUDA events recorded on
     # that stream around every kernel (dgppo_prof_*); not part of `value`
     ms_prof = timed(lambda: step_resident(True), 1)
@@ -301,10 +347,6 @@ def run_gpu(args):
     maxs = (C.c_float * 4)()
     _lib.check(_lib.lib().dgppo_prof_read(prof, sums, maxs), "dgppo_prof_read")
     kern_ms = {k: float(sums[i]) for i, k in enumerate(("policy", "step", "lidar", "graph"))}
-
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
 
     # the same through the full public call: algo.collect(params, keys) = device-side reset (K0 rejection
     # sampler) + LiDAR + graph + rollout.  Reported beside the metric; the metric itself uses synthetic states.
@@ -316,9 +358,10 @@ def run_gpu(args):
     except RuntimeError as exc:       # e.g. C5 at the default area: the reference's sampler cannot place 64 + 64
         ms_api, api_err = None, str(exc)
 
-    # update pre-pass (dgppo.py:204-273) on the record just collected: Vl scan,
-    # Vh over all (b, T+1) graphs, Dec-OCP GAE, CBF advantage merge.  Reported beside the metric.
-    prepass = None
+    # update (dgppo.py:136-321) on the record just collected: the pre-pass
+    # (Vl scan, Vh over all (b, T+1) graphs, Dec-OCP GAE, CBF advantage merge, deterministic rollout) and the
+    # PPO minibatch scan with its gradient all-reduce.  Reported beside the metric.
+    upd = None
     if not args.no_prepass:
         if ms_api is not None:
             ro = algo.collect(algo.params, keys, record=record)
@@ -339,70 +382,103 @@ def run_gpu(args):
         Vh, ms_vh = ev_time(lambda: algo._value_record("Vh", ro, None))
         (Qh, Ql), ms_gae = ev_time(lambda: algo.gae(ro.costs, -ro.rewards, Vh, Vl))
         _, ms_cbf = ev_time(lambda: algo.cbf_advantage(Ql, Vl, Vh, 0))
+        ms_pre = ms_upd = None
         try:
+            _, ms_pre = ev_time(lambda: algo.prepass(ro, 0))
             _, ms_upd = ev_time(lambda: algo.update(ro, 0))
         except RuntimeError:               # the deterministic rollout resets through the sampler (C5: infeasible area)
-            ms_upd = None
-        prepass = {"ms": {"scan_Vl": ms_vl, "Vh": ms_vh, "gae": ms_gae, "cbf_advantage": ms_cbf,
-                          "update_prepass_total": ms_upd},
-                   "graphs": b * (T + 1), "note": "components: one pass over the stochastic record; update_prepass_total = "
-                   "algo.update(): deterministic rollout (incl. reset) + Vl scan + Vh and GAE on both records + "
-                   "CBF advantage merge (dgppo.py:136-273), no gradient step"}
+            pass
+        gae_bytes = 4 * (T * n * 2 + T + (T + 1) * n * 2 + (T + 1) + T * n * 2 + T)
+        upd = {"ms": {"scan_Vl": ms_vl, "Vh": ms_vh, "gae": ms_gae, "cbf_advantage": ms_cbf,
+                      "prepass_total": ms_pre, "update_total": ms_upd},
+               "graphs": b * (T + 1), "minibatches": max(1, b // max(1, (algo.batch_size // world) // T)),
+               "gae_gbs": gae_bytes * b / (ms_gae * 1e-3) / 1e9,
+               "note": "components: one pass over the stochastic record; prepass_total = deterministic rollout (incl. "
+               "reset) + Vl scan + Vh and GAE on both records + CBF advantage merge (dgppo.py:136-273); "
+               "update_total = algo.update(): pre-pass + the PPO minibatch scan (update_Vl, update_Vh, update_policy "
+               "with torch-autograd gradients, flat gradient all-reduce over the ranks, clip, Adam)"}
         del Vl, Vh, Qh, Ql, ro
 
-    units = b * T * n * world
-    value = units * args.steps / (ms * 1e-3)
-    e2e = units * args.steps / (ms_e2e * 1e-3)
-
+    line = None
     if rank == 0:
         hbm, which = peaks()
-        # dominant kernel: the policy forward (K4a).  Algorithmic bytes per env-step:
-        # nodes + edges + recv + send + rnn in/out + eps + action + log_pi
-        pol_bytes = 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + 2 * d.n_edges + 2 * n * 64 + n * 2 + n * 2 + n)
-        ach = pol_bytes * b / (kern_ms["policy"] / T * 1e-3) / 1e9
+        sd, k_top = d.state_dim, (env.params.get("top_k_rays", 0) if lidar else 0)
+        n_obs_pts = n * k_top if lidar else w["obs"]
+        # ALGORITHMIC bytes per env-step of each kernel
+        by = {
+            "step": 4 * (n * sd + n * sd + n * 2 + n_obs_pts * (2 if lidar else 4) + n * sd + 1 + n * 2),
+            "lidar": 4 * (n * 2 + w["obs"] * 13 + n * k_top * 2) if lidar else 0,
+            "graph": 4 * (n * sd + n * sd + n_obs_pts * (2 if lidar else 4) + d.n_nodes * d.node_dim + d.n_edges * 4
+                          + d.n_nodes * sd + 2 * d.n_edges + d.n_nodes + 2),
+            # nodes + edges + recv + send + rnn in/out + eps + action + log_pi
+            "policy": 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + 2 * d.n_edges + 2 * n * 64 + n * 2 + n * 2 + n),
+        }
+        per_launch_us = {k: kern_ms[k] / T * 1e3 for k in kern_ms}
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # FFMA lanes x 2 flop x max SM clock, TFLOP/s
+        rk = {}
+        for k in ("step", "graph", "lidar", "policy"):
+            if by[k] == 0 or per_launch_us[k] <= 0:
+                continue
+            gbs = by[k] * b / (per_launch_us[k] * 1e-6) / 1e9
+            rk[k] = {"bound": "hbm" if k in ("step", "graph") else "fp32 issue", "algorithmic_bytes_per_launch": by[k] * b,
+                     "us_per_launch": per_launch_us[k], "achieved_gbs": gbs, "frac_of_hbm": gbs / hbm}
+        if args.workload == "C3":       # MAC counts of DESIGN.md section 4 (regrouped GNN 0.22 M + head 0.30 M per env-step)
+            flops = 2 * 0.52e6 * b
+            rk["policy"]["fp32_tflops"] = flops / (per_launch_us["policy"] * 1e-6) / 1e12
+            rk["policy"]["frac_of_fp32_peak"] = rk["policy"]["fp32_tflops"] / fp32_peak
+            rk["policy"]["note"] = ("head GEMMs run as 3xTF32 on tcgen05 (0.79 M tensor MAC per env-step), the GNN "
+                                    "layers on the FFMA pipe; counted here as the fp32 work they replace")
+        if upd is not None:
+            rk["gae"] = {"bound": "hbm", "achieved_gbs": upd["gae_gbs"], "frac_of_hbm": upd["gae_gbs"] / hbm,
+                         "us_per_launch": upd["ms"]["gae"] * 1e3}
+        tr = traffic_record(args.workload, b)
+        ach = rk["policy"]["achieved_gbs"]
         rec_bytes = 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + d.n_nodes * d.state_dim + 2 * d.n_edges
                          + d.n_nodes + 2 + n * 2 + n * 64 + 1 + n * 2 + n) + 1
-        rollout_gbs = rec_bytes * b * T / (ms / args.steps * 1e-3) / 1e9
+        rollout_gbs = rec_bytes * b * world * T / (ms / args.steps * 1e-3) / 1e9
+        chunks = algo._n_chunks(b)
+        kernels_per_rollout = chunks * (5 if lidar else 4) * T + (2 if lidar else 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['env']} n={n} obs={w['obs']} 32 rays, "
-                                   f"{b} envs/GPU x T={T} (one step = one full rollout)",
+                                   + (f"{b * world} envs in total, {b} envs/GPU" if args.scaling == "strong"
+                                      else f"{b} envs/GPU") + f" x T={T} (one step = one full rollout)",
                        "l2": "record written per step is %.1f GB >> 126 MB L2" % (record.nbytes() / 1e9)},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            # our kernels inside the timed region, per rollout: every env group (stream) launches
-            # T x {gnn_layers, head, env_step, [lidar], build_graph}; the reset graph adds [lidar] + build_graph
-            "gpu_launches": args.steps * (algo._n_chunks(b) * (5 if lidar else 4) * T + (2 if lidar else 1)),
+            "e2e": e2e,
+            # our kernels inside the timed region, per rollout and rank: every env group replays its captured
+            # graph of T x {gnn_layers, head_tc, env_step, [lidar], build_graph}; the reset graph adds
+            # [lidar] + build_graph.  host_launches: what the host submits (graph launches + reset kernels)
+            "gpu_launches": args.steps * kernels_per_rollout,
+            "host_launches": args.steps * (chunks + (2 if lidar else 1)),
             "clocks": clocks,
-            "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_kernel_wide", "bound": "hbm",
+            "roofline": {"kernel": "K4a policy forward = gnn_layers_kernel<2> + head_tc_kernel", "bound": "hbm",
                          "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         # dram__bytes_read + dram__bytes_write per launch pair from the committed ncu --set full
-                         # capture (C3, 4096 envs): gnn_layers 27.63 MB + head 17.51 MB read, 0.03 MB written
-                         "traffic": 45.17e6 if (args.workload == "C3" and b == 4096) else None,
-                         "traffic_source": "profiles/r1_all_v6.ncu.txt",
-                         "algorithmic_bytes_per_launch": pol_bytes * b,
+                         "traffic": (tr["policy_pair_bytes"] if tr else None),
+                         "traffic_source": (f"profiles/traffic.json (ncu --set full at commit {tr['commit']})" if tr else None),
+                         "algorithmic_bytes_per_launch": by["policy"] * b,
                          "peak_source": which,
-                         "note": "FP32-FFMA bound kernel reported against HBM as BASELINE's metric asks; "
-                                 "see DESIGN.md for the compute roofline"},
+                         "note": "issue / tensor bound kernel pair reported against HBM as BASELINE's metric asks; "
+                                 "roofline_per_kernel has the HBM-bound kernels and the compute view"},
+            "roofline_per_kernel": rk,
             "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof),
-            "rollout_streams": algo._n_chunks(b),
+            "rollout_streams": chunks,
             "api_collect_with_reset": ({"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT}
                                        if ms_api is not None else {"unavailable": api_err}),
             "rollout_hbm": {"unique_record_bytes_per_env_step": rec_bytes, "achieved_gbs": rollout_gbs,
-                            "frac_of_hbm": rollout_gbs / hbm},
+                            "frac_of_hbm": rollout_gbs / (hbm * world)},
         }
-        if prepass is not None:
-            line["update_prepass"] = prepass
+        if upd is not None:
+            line["update"] = upd
         if not args.no_cpu and world == 1:
-            rate, sample, cores = cpu_rollout_rate(w, target_s=12.0)
+            rate, sample, cores = cpu_rollout_rate(w, rounds=2)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": sample}
-        print(json.dumps(line))
     _lib.lib().dgppo_prof_destroy(prof)
-    if world > 1:
-        dist.destroy_process_group()
+    del record, algo
+    torch.cuda.empty_cache()
+    return {"line": line, "value": value, "ms_per_step": ms / args.steps, "e2e": e2e}
 
 
 def main():
@@ -414,7 +490,8 @@ def main():
     ap.add_argument("--workload", type=str, default="C3", choices=list(WORKLOADS))
     ap.add_argument("--no-prepass", action="store_true", help="skip the update pre-pass timing (Vl / Vh / GAE / CBF)")
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
-    ap.add_argument("--scaling", type=str, default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", type=str, default="strong", choices=["weak", "strong"],
+                    help="strong (default): the workload's envs in total, sharded over the ranks; weak: per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -21,7 +21,8 @@ class DgppoEnvCfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_agents", C.c_int32), ("n_obs", C.c_int32),
                 ("n_rays", C.c_int32), ("top_k", C.c_int32), ("reserved_", C.c_int32),
                 ("comm_radius", C.c_double), ("car_radius", C.c_double), ("obs_radius", C.c_double),
-                ("area_size", C.c_double), ("dt", C.c_double), ("dist2goal", C.c_double)]
+                ("area_size", C.c_double), ("dt", C.c_double), ("dist2goal", C.c_double),
+                ("connect_radius", C.c_double), ("goal_table", C.c_void_p)]
 
 
 class DgppoGraphDims(C.Structure):
@@ -40,7 +41,7 @@ class DgppoNetLayout(C.Structure):
                                           "tc_head", "total")])
 
 
-ABI_VERSION = 5        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
+ABI_VERSION = 6        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
 
 _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 
@@ -58,6 +59,8 @@ OBS_STRIDE = 16
 SIGNATURES = {
     "dgppo_abi_version": (C.c_int, []),
     "dgppo_graph_dims": (C.c_int, [C.POINTER(DgppoEnvCfg), C.POINTER(DgppoGraphDims)]),
+    "dgppo_n_goals": (C.c_int, [C.POINTER(DgppoEnvCfg)]),
+    "dgppo_n_cost": (C.c_int, [C.POINTER(DgppoEnvCfg)]),
     "dgppo_reset": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), _fp, C.c_double, C.c_double, C.c_double, C.c_double,
                               _fp, _fp, _fp, _fp, C.c_int32]),
     "dgppo_env_step": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), _fp, _fp, _fp, _fp, _fp, _fp, _fp,

@@ -455,7 +455,7 @@ class DGPPO(Algorithm):
         info["policy/log_pi_min"] = rollout.log_pis.min()
         info["Vl/max_target"], info["Vl/min_target"] = pp["bT_Ql"].max(), pp["bT_Ql"].min()
         info["eval/safe_data"] = pp["bTa_is_safe"].float().mean()
-        return {k: float(v) for k, v in info.items()}
+        return {k: float(v.detach()) if isinstance(v, torch.Tensor) else float(v) for k, v in info.items()}
 
     # ---------------------------------------------------------------- save / load
     def save(self, save_dir: str, step: int):

@@ -56,19 +56,32 @@ inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-__host__ __device__ inline bool is_mpe(int kind) {
-  return kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_TARGET || kind == DGPPO_ENV_MPE_CORRIDOR;
+__host__ __device__ inline bool is_lidar(int kind) {
+  return kind == DGPPO_ENV_LIDAR_SPREAD || kind == DGPPO_ENV_LIDAR_TARGET ||
+         kind == DGPPO_ENV_LIDAR_BICYCLE_TARGET || kind == DGPPO_ENV_LIDAR_LINE;
 }
-__host__ __device__ inline bool is_lidar(int kind) { return !is_mpe(kind); }
-__host__ __device__ inline bool is_spread(int kind) {
-  return kind == DGPPO_ENV_LIDAR_SPREAD || kind == DGPPO_ENV_MPE_SPREAD || kind == DGPPO_ENV_MPE_CORRIDOR;
+__host__ __device__ inline bool is_mpe(int kind) { return !is_lidar(kind); }
+// paired goals (one goal per agent, one agent-goal edge each); every other kind connects each agent to every goal node
+__host__ __device__ inline bool is_target(int kind) {
+  return kind == DGPPO_ENV_LIDAR_TARGET || kind == DGPPO_ENV_LIDAR_BICYCLE_TARGET || kind == DGPPO_ENV_MPE_TARGET;
+}
+__host__ __device__ inline bool is_spread(int kind) { return !is_target(kind); }
+__host__ __device__ inline bool is_line(int kind) { return kind == DGPPO_ENV_LIDAR_LINE || kind == DGPPO_ENV_MPE_LINE; }
+// goal NODES (landmarks for the Line / Formation families: lidar_line.py:36, mpe_line.py:36, mpe_formation.py:36)
+__host__ __device__ inline int n_goals_of(int kind, int n) {
+  return is_line(kind) ? 2 : (kind == DGPPO_ENV_MPE_FORMATION ? 1 : n);
+}
+__host__ __device__ inline int n_cost_of(int kind) { return kind == DGPPO_ENV_MPE_CONNECT_SPREAD ? 3 : 2; }
+// agent-obstacle edges always on, y range doubled (mpe_corridor.py:64-67,93; mpe_connect_spread.py:140-143,168)
+__host__ __device__ inline bool is_tall_mpe(int kind) {
+  return kind == DGPPO_ENV_MPE_CORRIDOR || kind == DGPPO_ENV_MPE_CONNECT_SPREAD;
 }
 __host__ __device__ inline bool is_bicycle(int kind) { return kind == DGPPO_ENV_LIDAR_BICYCLE_TARGET; }
 
 __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
   GraphDims d;
   d.n = c.n_agents;
-  d.g = c.n_agents;
+  d.g = n_goals_of(c.kind, c.n_agents);
   d.sd = is_bicycle(c.kind) ? 5 : 4;
   d.nd = d.sd + 3;
   const bool lid = is_lidar(c.kind);
@@ -87,8 +100,11 @@ int launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent, const
 
 inline int check_env_cfg(const DgppoEnvCfg* c) {
   if (!c) return DGPPO_EINVAL;
-  if (c->kind < 0 || c->kind > 5) return DGPPO_ENOTSUP;
+  if (c->kind < 0 || c->kind > 9) return DGPPO_ENOTSUP;
   if (c->kind == DGPPO_ENV_MPE_CORRIDOR && c->n_obs != 2) return DGPPO_EINVAL;       // mpe_corridor.py:33-35
+  if (c->kind == DGPPO_ENV_MPE_CONNECT_SPREAD && c->n_obs != 1) return DGPPO_EINVAL; // mpe_connect_spread.py:38-40
+  if (is_line(c->kind) && c->n_agents < 2) return DGPPO_EINVAL;                      // n - 1 intervals between the landmarks
+  if (c->kind == DGPPO_ENV_MPE_FORMATION && !c->goal_table) return DGPPO_EINVAL;
   if (c->n_agents < 1 || c->n_obs < 0) return DGPPO_EINVAL;
   if (is_lidar(c->kind) && c->n_obs > 0) {
     if (c->n_rays < 1 || c->n_rays > 1024) return DGPPO_ENOTSUP;

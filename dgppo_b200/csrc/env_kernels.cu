@@ -11,8 +11,9 @@ namespace dgppo {
 
 struct EnvConsts {
   int kind, n, n_obs, n_rays, top_k;
-  float dt, R, R_diag, R_obs, R_mpe_obs, car2, car, car_obs, d2g;
+  float dt, R, R_diag, R_obs, R_mpe_obs, car2, car, car_obs, d2g, connect_r;
   float lo[5], hi[5];
+  const float* goal_table;     // MPEFormation: (n, 2) goal offsets from the landmark
 };
 
 static EnvConsts make_consts(const DgppoEnvCfg& c) {
@@ -23,7 +24,10 @@ static EnvConsts make_consts(const DgppoEnvCfg& c) {
   k.R_diag = (float)(c.comm_radius + 1.0);          // lidar_spread.py:64
   k.R_obs = (float)(c.comm_radius - 1e-1);          // lidar_spread.py:87
   // MPE agent-obstacle edges: within comm_radius (mpe_spread.py:73-75); always on in the corridor (x100: mpe_corridor.py:93)
-  k.R_mpe_obs = (float)(c.kind == DGPPO_ENV_MPE_CORRIDOR ? c.comm_radius * 100 : c.comm_radius);
+  // (and in the connect-spread env: mpe_connect_spread.py:168)
+  k.R_mpe_obs = (float)(is_tall_mpe(c.kind) ? c.comm_radius * 100 : c.comm_radius);
+  k.connect_r = (float)c.connect_radius;            // mpe_connect_spread.py:117
+  k.goal_table = c.goal_table;
   k.car2 = (float)(c.car_radius * 2.0);             // lidar_env/base.py:188
   k.car = (float)c.car_radius;                      // lidar_env/base.py:197
   k.car_obs = (float)(c.car_radius + c.obs_radius); // mpe/base.py:181
@@ -34,7 +38,7 @@ static EnvConsts make_consts(const DgppoEnvCfg& c) {
     for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
   } else {
     const float v = is_mpe(c.kind) ? 1.0f : 0.5f;   // mpe/base.py:243-246 | lidar_env/base.py:273-276
-    const float Ay = (c.kind == DGPPO_ENV_MPE_CORRIDOR) ? (float)(c.area_size * 2) : A;   // mpe_corridor.py:64-67
+    const float Ay = is_tall_mpe(c.kind) ? (float)(c.area_size * 2) : A;   // mpe_corridor.py:64-67, mpe_connect_spread.py:140-143
     const float lo[5] = {0.f, 0.f, -v, -v, 0.f}, hi[5] = {A, Ay, v, v, 0.f};
     for (int i = 0; i < 5; ++i) { k.lo[i] = lo[i]; k.hi[i] = hi[i]; }
   }
@@ -107,8 +111,25 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
   }
   __syncwarp();
 
-  // cost on the pre-step state (lidar_env/base.py:180-207, mpe/base.py:164-191)
+  // cost on the pre-step state (lidar_env/base.py:180-207, mpe/base.py:164-191, mpe_connect_spread.py:105-138)
   const bool lid = is_lidar(k.kind);
+  const int nh = n_cost_of(k.kind);
+  const bool clip_hi = lid || nh == 3;           // a_max = 1 as well (lidar_env/base.py:205, mpe_connect_spread.py:135)
+  float connect = -INFINITY;                     // max_i (min_dist_i - connect_radius), the third cost of every agent
+  if (nh == 3) {
+    for (int i = lane; i < n; i += 32) {
+      float mind = INFINITY;
+      for (int j = 0; j < n; ++j) {
+        float d = norm2(fsub(px[i], px[j]), fsub(py[i], py[j]));
+        d = fadd(d, (i == j) ? 1e6f : 0.f);
+        mind = fminf(mind, d);
+      }
+      connect = fmaxf(connect, fsub(mind, k.connect_r));
+    }
+    for (int o = 16; o; o >>= 1) connect = fmaxf(connect, __shfl_xor_sync(0xffffffffu, connect, o));
+    connect = (connect <= 0.f) ? fsub(connect, 0.5f) : fadd(connect, 0.5f);
+    connect = clampf(connect, -1.f, 1.f);
+  }
   for (int i = lane; i < n; i += 32) {
     const float xi = px[i], yi = py[i];
     float mind = INFINITY;
@@ -135,17 +156,33 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
     }
     c0 = (c0 <= 0.f) ? fsub(c0, 0.5f) : fadd(c0, 0.5f);
     c1 = (c1 <= 0.f) ? fsub(c1, 0.5f) : fadd(c1, 0.5f);
-    if (lid) { c0 = clampf(c0, -1.f, 1.f); c1 = (c1 != c1) ? c1 : clampf(c1, -1.f, 1.f); }
-    else     { c0 = fmaxf(c0, -1.f);       c1 = fmaxf(c1, -1.f); }
-    cost[((size_t)env * io_pitch * n + i) * 2 + 0] = c0;
-    cost[((size_t)env * io_pitch * n + i) * 2 + 1] = c1;
+    if (clip_hi) { c0 = clampf(c0, -1.f, 1.f); c1 = (c1 != c1) ? c1 : clampf(c1, -1.f, 1.f); }
+    else         { c0 = fmaxf(c0, -1.f);       c1 = fmaxf(c1, -1.f); }
+    float* co = cost + ((size_t)env * io_pitch * n + i) * nh;
+    co[0] = c0; co[1] = c1;
+    if (nh == 3) co[2] = connect;
   }
 
-  // reward (lidar_spread.py:35-52, lidar_target.py:35-52)
-  const float* gl = goal + (size_t)env * n * sd;
+  // reward (lidar_spread.py:35-52, lidar_target.py:35-52; Line / Formation: the n goals derived from the
+  // landmark nodes by landmark2goal, lidar_line.py:128-150, mpe_line.py:119-152, mpe_formation.py:93-116)
+  const int g_nodes = n_goals_of(k.kind, n);
+  const float* gl = goal + (size_t)env * g_nodes * sd;
   const bool spread = is_spread(k.kind);
+  const bool line = is_line(k.kind), formation = k.kind == DGPPO_ENV_MPE_FORMATION;
+  const bool short_line = k.kind == DGPPO_ENV_MPE_LINE && n <= 3;             // mpe_line.py:121-124
   for (int q = lane; q < n; q += 32) {
-    const float gx = gl[q * sd], gy = gl[q * sd + 1];
+    float gx, gy;
+    if (line) {        // l0 + k * (l1 - l0) / n_interval, op by op
+      const float dx = fsub(gl[sd], gl[0]), dy = fsub(gl[sd + 1], gl[1]);
+      const float kq = (float)(short_line ? q + 1 : q), ni = (float)(short_line ? n + 1 : n - 1);
+      gx = fadd(gl[0], fdiv(fmul(kq, dx), ni));
+      gy = fadd(gl[1], fdiv(fmul(kq, dy), ni));
+    } else if (formation) {
+      gx = fadd(gl[0], __ldg(k.goal_table + 2 * q));
+      gy = fadd(gl[1], __ldg(k.goal_table + 2 * q + 1));
+    } else {
+      gx = gl[q * sd]; gy = gl[q * sd + 1];
+    }
     float d;
     if (spread) {
       d = INFINITY;
@@ -466,8 +503,9 @@ build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
       m = dist < k.R; rcv = i; snd = j;
     } else if (e < nn + nag) {                               // lidar_spread.py:69-76 | lidar_target.py:69-76
       const int r = e - nn;
-      const int i = (d.n_ag == 1) ? r : r / g;
-      const int q = (d.n_ag == 1) ? r : r - i * g;
+      const bool paired = is_target(k.kind);                // one goal per agent (not: one goal NODE, as in Formation)
+      const int i = paired ? r : r / g;
+      const int q = paired ? r : r - i * g;
       const float* a = fa + i * 4; const float* c = fg + q * 4;
       f = make_float4(fsub(a[0], c[0]), fsub(a[1], c[1]), fsub(a[2], c[2]), fsub(a[3], c[3]));
       m = true; rcv = i; snd = n + q;
@@ -495,6 +533,16 @@ build_graph_kernel(EnvConsts k, GraphDims d, const float* __restrict__ agent,
 using namespace dgppo;
 
 extern "C" int dgppo_abi_version(void) { return DGPPO_ABI_VERSION; }
+
+extern "C" int dgppo_n_goals(const DgppoEnvCfg* cfg) {
+  if (!cfg || cfg->kind < 0 || cfg->kind > 9) return DGPPO_EINVAL;
+  return n_goals_of(cfg->kind, cfg->n_agents);
+}
+
+extern "C" int dgppo_n_cost(const DgppoEnvCfg* cfg) {
+  if (!cfg || cfg->kind < 0 || cfg->kind > 9) return DGPPO_EINVAL;
+  return n_cost_of(cfg->kind);
+}
 
 extern "C" int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out) {
   if (int rc = check_env_cfg(cfg)) return rc;

@@ -141,7 +141,7 @@ static int rollout_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg*
     if (rc) return fail(rc);
     mark(t, 1);
     rc = dgppo_env_step(stream, env, agent_cur, B->goal, obs_cur, B->actions + (size_t)t * n * 2,
-                        agent_nxt, B->rewards + t, B->costs + (size_t)t * n * 2, T, b);
+                        agent_nxt, B->rewards + t, B->costs + (size_t)t * n * n_cost_of(env->kind), T, b);
     if (rc) return fail(rc);
     mark(t, 2);
     if (ahead) {

@@ -1,17 +1,19 @@
 """Environment registry and factory (dgppo/env/__init__.py:9-53).
 
-The environments on BASELINE.json's configs are registered plus
-MPETarget and MPECorridor, the first of the "other env families through the same
-kernels" row; the remaining MPE / Lidar tasks and VMAS are outside this path.
+Every MPE and LidarEnv task of the reference's registry runs through the same kernels (SURVEY.md 8 and
+8f.4): the environments on BASELINE.json's configs plus MPETarget, MPECorridor, the landmark families
+(LidarLine, MPELine, MPEFormation) and MPEConnectSpread with its third cost.  VMAS is outside this path.
 """
 from typing import Optional
 
 from .base import MultiAgentEnv, StepResult
-from .envs import (LidarBicycleTarget, LidarEnv, LidarEnvState, LidarSpread, LidarTarget, MPE,
-                   MPECorridor, MPEEnvState, MPESpread, MPETarget, Rectangle)
+from .envs import (LidarBicycleTarget, LidarEnv, LidarEnvState, LidarLine, LidarSpread, LidarTarget, MPE,
+                   MPEConnectSpread, MPECorridor, MPEEnvState, MPEFormation, MPELine, MPESpread, MPETarget,
+                   Rectangle)
 
-# name -> class; the names are the reference's `--env` values
-ENV = {cls.__name__: cls for cls in (MPETarget, MPECorridor, MPESpread, LidarSpread, LidarTarget, LidarBicycleTarget)}
+# name -> class; the names are the reference's `--env` values (env/__init__.py:9-23: every MPE and LidarEnv task)
+ENV = {cls.__name__: cls for cls in (MPETarget, MPESpread, MPELine, MPEFormation, MPECorridor, MPEConnectSpread,
+                                     LidarSpread, LidarTarget, LidarLine, LidarBicycleTarget)}
 
 DEFAULT_MAX_STEP = 128
 

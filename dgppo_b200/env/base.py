@@ -123,7 +123,11 @@ class MultiAgentEnv(ABC):
             self.KIND, self._num_agents, int(p.get("n_obs", 0)), int(p.get("n_rays", 32)),
             int(p.get("top_k_rays", 8)), 0, float(p["comm_radius"]), float(p["car_radius"]),
             float(p.get("obs_radius", 0.05)), float(self._area_size), float(self._dt),
-            float(p["dist2goal"]))
+            float(p["dist2goal"]), float(p.get("connect_radius", 0.0)), self._goal_table_ptr())
+
+    def _goal_table_ptr(self):
+        """Device table the kernels need beside the scalars (MPEFormation: goal offsets); None otherwise."""
+        return None
 
     def graph_dims(self) -> _lib.DgppoGraphDims:
         d = _lib.DgppoGraphDims()

@@ -91,7 +91,7 @@ def _reset_kernel(env, seeds: np.ndarray, dev, obs_len=(0.0, 0.0), theta=(0.0, 0
     lidar = isinstance(env, LidarEnv)
     keys = torch.from_numpy(seeds.astype(np.int64)).to(dev)           # same 64 bits, signed container
     agent = torch.empty((b, n, sd), dtype=torch.float32, device=dev)
-    goal = torch.empty((b, n, sd), dtype=torch.float32, device=dev)
+    goal = torch.empty((b, env.num_goals, sd), dtype=torch.float32, device=dev)
     obst = torch.empty((b, n_obs, _lib.OBS_STRIDE if lidar else 4), dtype=torch.float32, device=dev) \
         if n_obs > 0 else None
     draws = torch.empty((b,), dtype=torch.int32, device=dev)
@@ -167,7 +167,7 @@ class _KernelEnv(MultiAgentEnv):
         dev = agent.device
         nxt = torch.empty_like(agent)
         reward = torch.empty((b,), dtype=torch.float32, device=dev)
-        cost = torch.empty((b, n, 2), dtype=torch.float32, device=dev)
+        cost = torch.empty((b, n, self.n_cost), dtype=torch.float32, device=dev)
         cfg = self.env_cfg()
         _lib.check(_lib.lib().dgppo_env_step(stream_ptr(), C.byref(cfg), ptr(agent), ptr(goal), ptr(obs_nodes),
                                               ptr(action), ptr(nxt), ptr(reward), ptr(cost), 1, b),
@@ -369,6 +369,23 @@ class LidarTarget(LidarEnv):
     KIND = 1
 
 
+class LidarLine(LidarSpread):
+    """dgppo/env/lidar_env/lidar_line.py: two landmark nodes; the n goals the reward uses lie evenly on the
+    segment between them (landmark2goal, :128-133).  Env kind 6."""
+    PARAMS = dict(LidarEnv.PARAMS)
+    KIND = 6
+
+    def __init__(self, num_agents, area_size=None, max_step=128, dt=0.03, params=None):
+        super().__init__(num_agents, area_size, max_step, dt, params)
+        self.num_goals = 2
+
+    def landmark2goal(self, landmarks: torch.Tensor) -> torch.Tensor:
+        """(…, 2, 2) landmark positions -> (…, n, 2) goals (lidar_line.py:128-133)."""
+        n_int = self.num_agents - 1
+        k = torch.arange(0, n_int + 1, device=landmarks.device, dtype=landmarks.dtype)[:, None]
+        return landmarks[..., 0:1, :] + k * (landmarks[..., 1:2, :] - landmarks[..., 0:1, :]) / n_int
+
+
 class LidarBicycleTarget(LidarTarget):
     """dgppo/env/lidar_env/lidar_bicycle_target.py."""
     PARAMS = dict(LidarEnv.PARAMS)
@@ -506,6 +523,79 @@ class MPETarget(MPE):
     PARAMS = {"car_radius": 0.05, "comm_radius": 0.5, "n_obs": 3, "obs_radius": 0.05,
               "default_area_size": 1.5, "dist2goal": 0.01}
     KIND = 4
+
+
+class MPELine(MPESpread):
+    """dgppo/env/mpe/mpe_line.py: two landmark nodes, goals on the segment between them (landmark2goal,
+    :119-128: interior points for n <= 3, end points included otherwise).  Env kind 7."""
+    PARAMS = dict(MPESpread.PARAMS)
+    KIND = 7
+
+    def __init__(self, num_agents, area_size=None, max_step=128, dt=0.03, params=None):
+        super().__init__(num_agents, area_size, max_step, dt, params)
+        self.num_goals = 2
+
+    def landmark2goal(self, landmarks: torch.Tensor) -> torch.Tensor:
+        n = self.num_agents
+        d = landmarks[..., 1:2, :] - landmarks[..., 0:1, :]
+        if n <= 3:
+            n_int, k = n + 1, torch.arange(1, n + 1, device=landmarks.device, dtype=landmarks.dtype)[:, None]
+        else:
+            n_int, k = n - 1, torch.arange(0, n, device=landmarks.device, dtype=landmarks.dtype)[:, None]
+        return landmarks[..., 0:1, :] + k * d / n_int
+
+
+class MPEFormation(MPESpread):
+    """dgppo/env/mpe/mpe_formation.py: one landmark node, goals on a circle of radius comm_radius around it
+    (landmark2goal, :93-96).  Env kind 8; the circle offsets travel to the kernels as a device table."""
+    PARAMS = dict(MPESpread.PARAMS)
+    KIND = 8
+
+    def __init__(self, num_agents, area_size=None, max_step=128, dt=0.03, params=None):
+        super().__init__(num_agents, area_size, max_step, dt, params)
+        self.num_goals = 1
+        self._goal_table = None
+
+    def goal_offsets(self) -> np.ndarray:
+        th = np.linspace(0, 2 * np.pi, self.num_agents + 1).astype(F)[:-1]
+        return (F(self._params["comm_radius"]) * np.stack([np.cos(th).astype(F), np.sin(th).astype(F)], -1)).astype(F)
+
+    def _goal_table_ptr(self):
+        if self._goal_table is None:
+            self._goal_table = dev_f32(self.goal_offsets(), require_cuda())
+        return self._goal_table.data_ptr()
+
+    def landmark2goal(self, landmarks: torch.Tensor, R: Optional[float] = None) -> torch.Tensor:
+        off = torch.as_tensor(self.goal_offsets(), device=landmarks.device)
+        return landmarks[..., 0:1, :] + off
+
+
+class MPEConnectSpread(MPESpread):
+    """dgppo/env/mpe/mpe_connect_spread.py: MPESpread with one large obstacle, agents and goals sampled as
+    connected groups on either side of it, the y range doubled, obstacle edges always on and a THIRD cost:
+    connectivity (max over agents of nearest-neighbour distance - connect_radius, :116-118).  Env kind 9."""
+    PARAMS = {"car_radius": 0.05, "comm_radius": 0.5, "default_area_size": 1.0, "dist2goal": 0.01,
+              "n_obs": 1, "obs_radius": 0.25, "connect_radius": 0.45}
+    KIND = 9
+
+    def __init__(self, num_agents, area_size=None, max_step=128, dt=0.03, params=None):
+        params = dict(type(self).PARAMS if params is None else params)
+        super().__init__(num_agents, area_size, max_step, dt, params)
+        if self._params["n_obs"] != 1:                                   # mpe_connect_spread.py:38-40
+            self._params["n_obs"] = 1
+            print("WARNING: n_obs is set to 1 for MPEConnectSpread.")
+
+    @property
+    def n_cost(self) -> int:
+        return 3
+
+    @property
+    def cost_components(self) -> Tuple[str, ...]:
+        return "agent collisions", "obs collisions", "connectivity"
+
+    def state_lim(self, state=None):
+        A = self.area_size
+        return torch.tensor([0., 0., -1., -1.]), torch.tensor([A, A * 2, 1., 1.])
 
 
 class MPECorridor(MPE):

@@ -56,7 +56,7 @@ class RolloutRecord:
         self.actions = torch.empty((b, T, n, 2), **f32)
         self.log_pis = torch.empty((b, T, n), **f32) if stochastic else None
         self.rewards = torch.empty((b, T), **f32)
-        self.costs = torch.empty((b, T, n, 2), **f32)
+        self.costs = torch.empty((b, T, n, env.n_cost), **f32)
         self.dones = torch.zeros((b, T), dtype=torch.bool, device=device)
         self.agent_ws = torch.empty((2, b, n, d.state_dim), **f32)
         self.hits_ws = self.hits_ws2 = None
@@ -159,7 +159,7 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
             obstacles = es.obstacle.record.contiguous()
             rays = env.ray_dirs(dev)
             k = env.params["top_k_rays"]
-            rec.hits_ws.copy_(graph0.states[:, 2 * n:2 * n + n * k, :2].reshape(b, n, k, 2))
+            rec.hits_ws.copy_(graph0.states[:, n + env.num_goals:n + env.num_goals + n * k, :2].reshape(b, n, k, 2))
     elif isinstance(es, MPEEnvState) and es.obs is not None:
         obstacles = es.obs.contiguous()
     if eps is not None:
@@ -206,8 +206,8 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
     def env_view(lo, hi):
         st = rec.states[:, lo:hi]
         if isinstance(es, LidarEnvState):
-            return LidarEnvState(st[:, :, :n], st[:, :, n:2 * n], es.obstacle)
-        return MPEEnvState(st[:, :, :n], st[:, :, n:2 * n], es.obs)
+            return LidarEnvState(st[:, :, :n], st[:, :, n:n + env.num_goals], es.obstacle)
+        return MPEEnvState(st[:, :, :n], st[:, :, n:n + env.num_goals], es.obs)
     rnn = rec.rnn[:, 1:] if test_mode else rec.rnn[:, :T]
     return Rollout(
         graph=rec.graph_view(0, T, env_view(0, T)),
@@ -274,8 +274,8 @@ def run_rollout_chunked(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state
     def env_view(lo, hi):
         stt = rec.states[:, lo:hi]
         if isinstance(es, LidarEnvState):
-            return LidarEnvState(stt[:, :, :n], stt[:, :, n:2 * n], es.obstacle)
-        return MPEEnvState(stt[:, :, :n], stt[:, :, n:2 * n], es.obs)
+            return LidarEnvState(stt[:, :, :n], stt[:, :, n:n + env.num_goals], es.obstacle)
+        return MPEEnvState(stt[:, :, :n], stt[:, :, n:n + env.num_goals], es.obs)
     rnn = rec.rnn[:, 1:] if test_mode else rec.rnn[:, :T]
     return Rollout(graph=rec.graph_view(0, T, env_view(0, T)), actions=rec.actions,
                    rnn_states=rnn.unsqueeze(2).unsqueeze(4), rewards=rec.rewards, costs=rec.costs, dones=rec.dones,

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DGPPO_ABI_VERSION 5
+#define DGPPO_ABI_VERSION 6
 
 /* negative error codes (positive values are cudaError_t) */
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
@@ -48,12 +48,19 @@ extern "C" {
 #define DGPPO_ENV_MPE_SPREAD            3  /* mpe/mpe_spread.py                  */
 #define DGPPO_ENV_MPE_TARGET            4  /* mpe/mpe_target.py (same kernels, paired goals) */
 #define DGPPO_ENV_MPE_CORRIDOR          5  /* mpe/mpe_corridor.py: MPESpread + 2 fixed obstacles, y <= 2 area, obstacle edges always on */
+/* the landmark families: the goal NODES are landmarks (2 for Line, 1 for Formation), the n goal positions
+ * the reward uses are derived from them (landmark2goal: lidar_line.py:128-133, mpe_line.py:119-128,
+ * mpe_formation.py:93-96); spread-type agent-goal edges to every landmark */
+#define DGPPO_ENV_LIDAR_LINE            6  /* lidar_env/lidar_line.py            */
+#define DGPPO_ENV_MPE_LINE              7  /* mpe/mpe_line.py                    */
+#define DGPPO_ENV_MPE_FORMATION         8  /* mpe/mpe_formation.py               */
+#define DGPPO_ENV_MPE_CONNECT_SPREAD    9  /* mpe/mpe_connect_spread.py: third cost column (connectivity), y <= 2 area, obstacle edges always on */
 
 /* Static environment description: the PARAMS dicts (lidar_spread.py:13-22,
  * mpe_spread.py:12-19) plus dt / num_agents (env/__init__.py:47-53). */
 typedef struct DgppoEnvCfg {
   int32_t kind;         /* DGPPO_ENV_*                                   */
-  int32_t n_agents;     /* n (== number of goals)                        */
+  int32_t n_agents;     /* n                                             */
   int32_t n_obs;        /* rectangles (Lidar*) or circles (MPE*)         */
   int32_t n_rays;       /* LiDAR beams per agent (default 32)            */
   int32_t top_k;        /* LiDAR returns kept per agent (default 8)      */
@@ -67,7 +74,17 @@ typedef struct DgppoEnvCfg {
   double area_size;     /* 1.5                                           */
   double dt;            /* 0.03                                          */
   double dist2goal;     /* 0.01                                          */
+  double connect_radius; /* 0.45 (MPEConnectSpread only)                 */
+  /* MPEFormation only, else NULL: DEVICE table (n, 2) f32 of the goal offsets comm_radius * [cos, sin](theta_k),
+   * theta = linspace(0, 2 pi, n + 1)[:-1] (mpe_formation.py:93-96) - data, like K2's ray table, so that no
+   * device libm enters a goal position */
+  const float* goal_table;
 } DgppoEnvCfg;
+
+/* goal nodes of an env kind: 2 (Line), 1 (Formation), else n_agents; cost columns: 3 (ConnectSpread), else 2.
+ * Every `goal` array below is (b, n_goals, state_dim) and every `cost` array (..., n, n_cost).              */
+int dgppo_n_goals(const DgppoEnvCfg* cfg);
+int dgppo_n_cost(const DgppoEnvCfg* cfg);
 
 /* Derived graph sizes (utils/graph.py:212-247 + each env's edge_blocks). */
 typedef struct DgppoGraphDims {

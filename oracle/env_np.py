@@ -25,6 +25,10 @@ LIDAR_BICYCLE_TARGET = 2  # dgppo/env/lidar_env/lidar_bicycle_target.py
 MPE_SPREAD = 3            # dgppo/env/mpe/mpe_spread.py
 MPE_TARGET = 4            # dgppo/env/mpe/mpe_target.py
 MPE_CORRIDOR = 5          # dgppo/env/mpe/mpe_corridor.py
+LIDAR_LINE = 6            # dgppo/env/lidar_env/lidar_line.py     (2 landmarks -> n goals on the segment)
+MPE_LINE = 7              # dgppo/env/mpe/mpe_line.py
+MPE_FORMATION = 8         # dgppo/env/mpe/mpe_formation.py        (1 landmark -> n goals on a circle)
+MPE_CONNECT_SPREAD = 9    # dgppo/env/mpe/mpe_connect_spread.py   (third cost: connectivity)
 
 KIND_BY_NAME = {
     "LidarSpread": LIDAR_SPREAD,
@@ -33,6 +37,10 @@ KIND_BY_NAME = {
     "MPESpread": MPE_SPREAD,
     "MPETarget": MPE_TARGET,
     "MPECorridor": MPE_CORRIDOR,
+    "LidarLine": LIDAR_LINE,
+    "MPELine": MPE_LINE,
+    "MPEFormation": MPE_FORMATION,
+    "MPEConnectSpread": MPE_CONNECT_SPREAD,
 }
 
 
@@ -52,10 +60,15 @@ class EnvCfg:
     dt: float = 0.03
     dist2goal: float = 0.01
     max_step: int = 128
+    connect_radius: float = 0.45
 
     @property
     def is_lidar(self) -> bool:
-        return self.kind not in (MPE_SPREAD, MPE_TARGET, MPE_CORRIDOR)
+        return self.kind in (LIDAR_SPREAD, LIDAR_TARGET, LIDAR_BICYCLE_TARGET, LIDAR_LINE)
+
+    @property
+    def n_cost(self) -> int:             # mpe_connect_spread.py:45-46
+        return 3 if self.kind == MPE_CONNECT_SPREAD else 2
 
     @property
     def is_bicycle(self) -> bool:
@@ -74,7 +87,11 @@ class EnvCfg:
         return 4
 
     @property
-    def n_goal(self) -> int:
+    def n_goal(self) -> int:             # goal NODES: landmarks for the Line / Formation families
+        if self.kind in (LIDAR_LINE, MPE_LINE):
+            return 2                     # lidar_line.py:36, mpe_line.py:36
+        if self.kind == MPE_FORMATION:
+            return 1                     # mpe_formation.py:36
         return self.n
 
     @property
@@ -91,7 +108,7 @@ class EnvCfg:
 
     @property
     def n_ag(self) -> int:               # goal senders per agent
-        return self.n_goal if self.kind in (LIDAR_SPREAD, MPE_SPREAD, MPE_CORRIDOR) else 1
+        return 1 if self.kind in (LIDAR_TARGET, LIDAR_BICYCLE_TARGET, MPE_TARGET) else self.n_goal
 
     @property
     def n_ao(self) -> int:               # obstacle senders per agent
@@ -240,7 +257,7 @@ def state_lim(cfg: EnvCfg) -> Tuple[np.ndarray, np.ndarray]:
     A = cfg.area
     if cfg.is_bicycle:
         return np.array([0, 0, -1, -1, -0.5], F), np.array([A, A, 1, 1, 0.5], F)
-    if cfg.kind == MPE_CORRIDOR:                       # mpe_corridor.py:64-67
+    if cfg.kind in (MPE_CORRIDOR, MPE_CONNECT_SPREAD):  # mpe_corridor.py:64-67, mpe_connect_spread.py:140-143
         return np.array([0, 0, -1, -1], F), np.array([A, A * 2, 1, 1], F)
     if not cfg.is_lidar:
         return np.array([0, 0, -1, -1], F), np.array([A, A, 1, 1], F)
@@ -294,12 +311,16 @@ def get_cost(cfg: EnvCfg, agent: np.ndarray, obs_nodes: Optional[np.ndarray]) ->
         d = norm2((px[:, :, None] - obs_nodes[:, None, :, 0]).astype(F),
                   (py[:, :, None] - obs_nodes[:, None, :, 1]).astype(F))
         obs_cost = (F(cfg.car_radius + cfg.obs_radius) - d.min(axis=2)).astype(F)
-    cost = np.stack([agent_cost, obs_cost], axis=-1)
+    cols = [agent_cost, obs_cost]
+    if cfg.kind == MPE_CONNECT_SPREAD:                  # connectivity cost (mpe_connect_spread.py:116-118)
+        connect = (min_dist - F(cfg.connect_radius)).astype(F).max(axis=1)
+        cols.append(np.broadcast_to(connect[:, None], (b, n)))
+    cost = np.stack(cols, axis=-1)
     eps = F(0.5)
     cost = np.where(cost <= 0.0, (cost - eps).astype(F), (cost + eps).astype(F)).astype(F)
-    if cfg.is_lidar:
+    if cfg.is_lidar or cfg.kind == MPE_CONNECT_SPREAD:  # clip to [-1, 1] (lidar_env/base.py:205, mpe_connect_spread.py:135)
         return np.clip(cost, F(-1.0), F(1.0))
-    return np.maximum(cost, F(-1.0))
+    return np.maximum(cost, F(-1.0))                    # a_min only (mpe/base.py:189)
 
 
 def get_reward(cfg: EnvCfg, agent: np.ndarray, goal: np.ndarray, action: np.ndarray) -> np.ndarray:
@@ -307,8 +328,10 @@ def get_reward(cfg: EnvCfg, agent: np.ndarray, goal: np.ndarray, action: np.ndar
     Target (lidar_target.py:35-52).  ``action`` is the CLIPPED action
     (lidar_env/base.py:160,170).  -> (b,)"""
     ax, ay = agent[..., 0], agent[..., 1]
+    if cfg.kind in (LIDAR_LINE, MPE_LINE, MPE_FORMATION):
+        goal = landmark2goal(cfg, goal[..., :2])
     gx, gy = goal[..., 0], goal[..., 1]
-    if cfg.kind in (LIDAR_SPREAD, MPE_SPREAD, MPE_CORRIDOR):
+    if cfg.kind not in (LIDAR_TARGET, LIDAR_BICYCLE_TARGET, MPE_TARGET):
         d = norm2((gx[:, :, None] - ax[:, None, :]).astype(F), (gy[:, :, None] - ay[:, None, :]).astype(F))
         dist2goal = d.min(axis=2)
     else:
@@ -320,6 +343,29 @@ def get_reward(cfg: EnvCfg, agent: np.ndarray, goal: np.ndarray, action: np.ndar
     an = norm2(action[..., 0], action[..., 1])
     reward = (reward - (seq_mean((an * an).astype(F)) * F(0.0001)).astype(F)).astype(F)
     return reward
+
+
+def formation_offsets(cfg: EnvCfg) -> np.ndarray:
+    """R * [cos, sin](linspace(0, 2 pi, n + 1)[:-1]) (mpe_formation.py:93-96), fp32: a per-env-config TABLE
+    (the kernels take it as data, like the LiDAR ray table, so no device libm enters the goal positions)."""
+    th = np.linspace(0, 2 * np.pi, cfg.n + 1).astype(F)[:-1]
+    return (F(cfg.comm_radius) * np.stack([np.cos(th).astype(F), np.sin(th).astype(F)], axis=-1)).astype(F)
+
+
+def landmark2goal(cfg: EnvCfg, lm: np.ndarray) -> np.ndarray:
+    """landmark2goal: the n goal positions the reward uses, from the landmark nodes lm (b, n_goal, 2).
+    Line (lidar_line.py:128-133, mpe_line.py:119-128): l0 + k * (l1 - l0) / n_interval; Formation
+    (mpe_formation.py:93-96): landmark + R [cos, sin](theta_k).  Each op rounded to fp32."""
+    n = cfg.n
+    if cfg.kind == MPE_FORMATION:
+        return (lm[:, 0:1, :] + formation_offsets(cfg)[None]).astype(F)
+    direction = (lm[:, 1] - lm[:, 0]).astype(F)
+    if cfg.kind == MPE_LINE and n <= 3:
+        n_int, ks = n + 1, np.arange(1, n + 1)
+    else:
+        n_int, ks = n - 1, np.arange(0, n)
+    step = ((ks.astype(F)[None, :, None] * direction[:, None, :]).astype(F) / F(n_int)).astype(F)
+    return (lm[:, 0:1, :] + step).astype(F)
 
 
 # -------------------------------------------------------------------- graph
@@ -424,7 +470,8 @@ def get_graph(cfg: EnvCfg, agent: np.ndarray, goal: np.ndarray,
             d = norm2((px[:, :, None] - obs_nodes[:, None, :, 0]).astype(F),
                       (py[:, :, None] - obs_nodes[:, None, :, 1]).astype(F))
             # within comm_radius (mpe_spread.py:73-75); always on in the corridor (x100: mpe_corridor.py:93)
-            active = d < (F(cfg.comm_radius * 100) if cfg.kind == MPE_CORRIDOR else R)
+            # (also x100 in the connect-spread env: mpe_connect_spread.py:168)
+            active = d < (F(cfg.comm_radius * 100) if cfg.kind in (MPE_CORRIDOR, MPE_CONNECT_SPREAD) else R)
             edges[:, off:off + n * o] = ao.reshape(b, n * o, 4)
             sid = n + g + np.arange(o, dtype=np.int32)
             recv[:, off:off + n * o] = np.where(active, ids[None, :, None], pad).reshape(b, n * o)

@@ -251,6 +251,11 @@ def uniform(key, shape=(), dtype=np.float32, minval=0.0, maxval=1.0):
     return _narrow((u * (hi - lo) + lo).astype(np.float32))
 
 
+def randint(key, shape, minval, maxval, dtype=np.int32):
+    """jax.random.randint: integers in [minval, maxval) (mpe_line.py:65, lidar_line.py:61)."""
+    return _narrow(_gen(key).integers(int(minval), int(maxval), size=shape).astype(np.int32))
+
+
 def normal(key, shape=(), dtype=np.float32):
     return _narrow(_gen(key).standard_normal(size=shape).astype(np.float32))
 
@@ -348,7 +353,7 @@ def install(reference_root: str = REFERENCE_ROOT):
     if "jax" in sys.modules and getattr(sys.modules["jax"], "__shim__", False):
         return
     jnp = _module("jax.numpy", **_build_jnp())
-    jr = _module("jax.random", PRNGKey=PRNGKey, split=split, uniform=uniform, normal=normal, key=PRNGKey)
+    jr = _module("jax.random", PRNGKey=PRNGKey, split=split, uniform=uniform, normal=normal, randint=randint, key=PRNGKey)
     lax = _module("jax.lax", scan=scan, while_loop=while_loop,
                   cond=lambda p, t, f, *a: t(*a) if p else f(*a), stop_gradient=lambda x: x)
     jtu = _module("jax.tree_util", tree_map=tree_map, tree_flatten=tree_flatten, tree_unflatten=tree_unflatten,

@@ -130,3 +130,150 @@ def reset_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3), theta_range=N
             th = F(u[0] * F(6.283185307179586))
             agent[i, 2], agent[i, 3] = np.cos(th), np.sin(th)
     return agent, goal, obst, rng.ctr
+
+
+# --------------------------------------------------------------------------------------------------
+# Landmark families + connected spread (env kinds 6-9): LidarLine.reset (lidar_line.py:38-126), MPELine.reset
+# (mpe_line.py:38-117), MPEFormation.reset (mpe_formation.py:38-91), MPEConnectSpread.reset
+# (mpe_connect_spread.py:52-103), on the counter stream and in the draw order of reset_landmark_kernel.
+def _sample_nodes(rng, n, min_dist, ax, ay, area):
+    """get_node_goal_rng without obstacles -> st, gl, ok"""
+    st, gl = np.zeros((n, 2), F), np.zeros((n, 2), F)
+    agent_id = restarts = 0
+    while agent_id < n:
+        u = rng.next2()
+        c = (F(u[0] * ax), F(u[1] * ay))
+        it_a = 0
+        while it_a < MAX_ITER and _collides(c, st, min_dist):
+            it_a += 1
+            u = rng.next2()
+            c = (F(u[0] * ax), F(u[1] * ay))
+        st[agent_id] = c
+        u = rng.next2()
+        g = (F(u[0] * ax), F(u[1] * ay))
+        it_g = 0
+        while it_g < MAX_ITER and (_collides(g, gl, min_dist) or g[0] < 0 or g[1] < 0 or g[0] > area or g[1] > area):
+            it_g += 1
+            u = rng.next2()
+            g = (F(u[0] * ax), F(u[1] * ay))
+        gl[agent_id] = g
+        agent_id += 1
+        if it_a >= MAX_ITER or it_g >= MAX_ITER:
+            restarts += 1
+            if restarts > MAX_RESTARTS:
+                continue
+            agent_id = 0
+            st[:] = 0
+            gl[:] = 0
+    return st, gl, restarts <= MAX_RESTARTS
+
+
+def _badly_spaced(p, lo, hi):
+    n = len(p)
+    d = env_np.norm2((p[:, None, 0] - p[None, :, 0]).astype(F), (p[:, None, 1] - p[None, :, 1]).astype(F))
+    d = (d + (np.eye(n, dtype=F) * F(1e6)).astype(F)).astype(F)
+    m = d.min(axis=1)
+    return bool(((m > F(hi)) | (m < F(lo))).any())
+
+
+def reset_landmark_states(cfg: env_np.EnvCfg, key: int, obs_len=(0.1, 0.3)):
+    """-> agent (n, 4), goal nodes (n_goal, 4), obstacle record (n_obs, 16) | mpe obs (n_obs, 4), n_draws (-1: gave up)"""
+    rng = Rng(key)
+    n, A = cfg.n, F(cfg.area)
+    car, obr = F(cfg.car_radius), F(cfg.obs_radius)
+    ok = True
+    agent = np.zeros((n, 4), F)
+    if cfg.kind == env_np.MPE_CONNECT_SPREAD:
+        side_y = F((cfg.area - cfg.obs_radius * 2) / 2 - 1.5 * cfg.car_radius)
+        shift = F(cfg.area - (cfg.area - cfg.obs_radius * 2) / 2 + 1.5 * cfg.car_radius)
+        tries = 0
+        while True:
+            st, gl, ok = _sample_nodes(rng, n, F(2.3 * cfg.car_radius), A, side_y, A)
+            gl[:, 1] = (gl[:, 1] + shift).astype(F)
+            tries += 1
+            if not (ok and tries < 4096 and (_badly_spaced(st, F(car * F(2)), cfg.connect_radius)
+                                             or _badly_spaced(gl, 0.0, cfg.connect_radius))):
+                break
+        if tries >= 4096:
+            ok = False
+        u = rng.next2()
+        obst = np.zeros((1, 4), F)
+        obst[0, 0] = F(F(u[0] * F(F(A - obr) - obr)) + obr)
+        obst[0, 1] = F(A / F(2))
+        goal = np.zeros((n, 4), F)
+        agent[:, :2], goal[:, :2] = st, gl
+        return agent, goal, obst, (rng.ctr if ok else -1)
+
+    st, _, ok = _sample_nodes(rng, n, F(2.0 * cfg.car_radius), A, A, A)
+    short_line = cfg.kind == env_np.MPE_LINE and n <= 3
+    if cfg.kind == env_np.MPE_FORMATION:
+        lo = F(cfg.comm_radius + 2 * cfg.car_radius)
+        hi = F(cfg.area - cfg.comm_radius - 2 * cfg.car_radius)
+        u = rng.next2()
+        lm = np.array([[F(F(u[0] * F(hi - lo)) + lo), F(F(u[1] * F(hi - lo)) + lo)]], F)
+    else:
+        lm_min = (n * 5 * cfg.car_radius) if short_line else ((n - 2) * 6 * cfg.car_radius)
+        u = rng.next2()
+        if short_line:
+            l0 = (F(u[0] * A), F(u[1] * A))
+        else:
+            side = F(cfg.area - lm_min)
+            half = F(A / F(2))
+            cx = F(F(F(u[0] * F(A - side)) - half) + F(0))
+            cy = F(F(F(u[1] * side) - F(0)) + F(half - side))
+            r = rng.next2()
+            region = min(3, int(F(r[0] * F(4))))
+            rx, ry = [(cx, cy), (-cy, cx), (-cx, -cy), (cy, -cx)][region]
+            l0 = (F(rx + half), F(ry + half))
+        u = rng.next2()
+        l1 = (F(u[0] * A), F(u[1] * A))
+        guard = 0
+        while guard < (1 << 16) and env_np.norm2(F(l1[0] - l0[0]), F(l1[1] - l0[1])) < F(lm_min):
+            guard += 1
+            u = rng.next2()
+            l1 = (F(u[0] * A), F(u[1] * A))
+        if guard >= (1 << 16):
+            ok = False
+        lm = np.array([l0, l1], F)
+    eg = env_np.landmark2goal(cfg, lm[None])[0]
+    if cfg.kind == env_np.LIDAR_LINE:
+        r = F(car * F(1.1))
+        lo_, hi_ = F(obs_len[0]), F(obs_len[1])
+        obst = np.zeros((cfg.n_obs, 16), F)
+        pts = np.concatenate([st, eg], axis=0)
+        for o in range(cfg.n_obs):
+            guard = 0
+            while True:
+                c, l, t = rng.next2(), rng.next2(), rng.next2()
+                cx, cy = F(c[0] * A), F(c[1] * A)
+                w = F(lo_ + F(l[0] * F(hi_ - lo_)))
+                h = F(lo_ + F(l[1] * F(hi_ - lo_)))
+                th = F(t[0] * F(3.14159274101257324))
+                rc = env_np.rect_create(np.array([cx, cy], F), w, h, th)
+                rec = np.zeros(16, F)
+                rec[0:2] = [cx, cy]
+                rec[2:7] = [w, h, th, rc["cos"], rc["sin"]]
+                rec[8:16] = rc["points"].reshape(8)
+                bad = any(_inside_any(p, rec[None], r) for p in pts)
+                guard += 1
+                if not (bad and guard < (1 << 16)):
+                    break
+            if guard >= (1 << 16):
+                ok = False
+            obst[o] = rec
+    else:
+        obst = np.zeros((cfg.n_obs, 4), F)
+        lo, hi = F(car * F(3)), F(A - F(car * F(3)))
+        for o in range(cfg.n_obs):
+            u = rng.next2()
+            p = (F(u[0] * A), F(u[1] * A))
+            guard = 0
+            while guard < (1 << 20) and (_collides(p, st, F(car + obr)) or _collides(p, eg, F(F(car * F(2)) + obr))
+                                         or p[0] < lo or p[1] < lo or p[0] > hi or p[1] > hi):
+                guard += 1
+                u = rng.next2()
+                p = (F(lo + F(u[0] * F(hi - lo))), F(lo + F(u[1] * F(hi - lo))))
+            obst[o, 0:2] = p
+    goal = np.zeros((cfg.n_goal, 4), F)
+    agent[:, :2], goal[:, :2] = st, lm
+    return agent, goal, obst, (rng.ctr if ok else -1)

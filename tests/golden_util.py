@@ -18,6 +18,11 @@ CASES = {
     "LidarSpread_n4_obs0": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=4, n_obs=0),
     "MPETarget_n6_obs3": env_np.EnvCfg(env_np.MPE_TARGET, n=6, n_obs=3),
     "MPECorridor_n5_obs2": env_np.EnvCfg(env_np.MPE_CORRIDOR, n=5, n_obs=2, area=1.0, obs_radius=0.2),
+    "LidarLine_n4_obs3": env_np.EnvCfg(env_np.LIDAR_LINE, n=4, n_obs=3),
+    "MPELine_n3_obs3": env_np.EnvCfg(env_np.MPE_LINE, n=3, n_obs=3),
+    "MPELine_n5_obs3": env_np.EnvCfg(env_np.MPE_LINE, n=5, n_obs=3),
+    "MPEFormation_n4_obs3": env_np.EnvCfg(env_np.MPE_FORMATION, n=4, n_obs=3),
+    "MPEConnectSpread_n3_obs1": env_np.EnvCfg(env_np.MPE_CONNECT_SPREAD, n=3, n_obs=1, area=1.0, obs_radius=0.25),
 }
 
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libdgppo_b200.so does not export {s}"
     assert set(syms) == set(_lib.SIGNATURES), (set(syms) ^ set(_lib.SIGNATURES))
-    assert lib.dgppo_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.dgppo_abi_version() == _lib.ABI_VERSION == 6
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -52,7 +52,7 @@ def test_survey_graph_sizes():
 def test_bad_configs_are_rejected():
     lib = _lib.lib()
     d = _lib.DgppoGraphDims()
-    bad = c_cfg(CONFIGS["C3"]); bad.kind = 7
+    bad = c_cfg(CONFIGS["C3"]); bad.kind = 10
     assert lib.dgppo_graph_dims(C.byref(bad), C.byref(d)) == _lib.lib().dgppo_graph_dims(C.byref(bad), C.byref(d)) == -2
     bad = c_cfg(CONFIGS["C3"]); bad.top_k = 64
     assert lib.dgppo_graph_dims(C.byref(bad), C.byref(d)) == -1

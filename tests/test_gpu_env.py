@@ -106,7 +106,7 @@ def test_empty_batch_and_bad_args():
     assert lib.dgppo_env_step(None, C.byref(cfg), None, None, None, None, None, None, None, 1, 0) == 0
     assert lib.dgppo_env_step(None, C.byref(cfg), None, None, None, None, None, None, None, 1, 4) == -1
     bad = util.c_cfg(CONFIGS["C3"])
-    bad.kind = 9
+    bad.kind = 10
     assert lib.dgppo_lidar(None, C.byref(bad), None, None, None, None, 4) == -2
 
 

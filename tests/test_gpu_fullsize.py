@@ -171,8 +171,8 @@ def test_full_size_update_prepass():
     cfg = CONFIGS[name]
     env, algo, g0, eps = _setup(env_id, n, obs, b, T, seed=9)
     ro = algo.collect(algo.params, None, eps=eps, graph0=g0)
-    info = algo.update(ro, step=0)
-    pp = algo.last_prepass
+    pp = algo.prepass(ro, step=0)
+    info = {"eval/safe_data": float(pp["bTa_is_safe"].float().mean())}
     Vl, Vh, Qh, Ql, A = pp["bTp1_Vl"], pp["bTp1ah_Vh"], pp["bTah_Qh"], pp["bT_Ql"], pp["bTa_A"]
     assert Vl.shape == (b, T + 1) and Vh.shape == (b, T + 1, n, 2) and Qh.shape == (b, T, n, 2) and A.shape == (b, T, n)
     for t in (Vl, Vh, Qh, Ql, A, pp["bTp1ah_Vh_det"], pp["bTah_Qh_det"]):

@@ -70,22 +70,25 @@ def _np_obstacles(rect):
 
 
 @pytest.mark.parametrize("env_id,n,obs", [("LidarSpread", 3, 3), ("LidarTarget", 4, 2), ("LidarBicycleTarget", 4, 3),
-                                          ("MPESpread", 5, 3), ("MPETarget", 6, 3), ("MPECorridor", 5, 2)])
+                                          ("MPESpread", 5, 3), ("MPETarget", 6, 3), ("MPECorridor", 5, 2),
+                                          ("LidarLine", 4, 3), ("MPELine", 3, 3), ("MPELine", 6, 2),
+                                          ("MPEFormation", 5, 3), ("MPEConnectSpread", 3, 1)])
 def test_env_api_reset_step(env_id, n, obs):
     from dgppo_b200.env import make_env
     env = make_env(env_id, num_agents=n, num_obs=obs)
     cfg = env_np.EnvCfg(env_np.KIND_BY_NAME[env_id], n=n, n_obs=obs, area=env.area_size,
                         obs_radius=env.params.get("obs_radius", 0.05))
+    assert env.n_cost == cfg.n_cost and env.num_goals == cfg.n_goal
     g = env.reset(np.arange(10))
     assert g.nodes.shape == (10, cfg.n_nodes, cfg.node_dim) and g.receivers.dtype == torch.int32
     # reset honours the reference's rejection rules (env/utils.py:169-204)
     pos = g.env_states.agent[..., :2].cpu().numpy()
     dmin = np.linalg.norm(pos[:, :, None] - pos[:, None], axis=-1) + np.eye(n) * 10
-    min_dist = (2.2 if env_id.startswith("Lidar") else 2.0) * 0.05
+    min_dist = (2.2 if env_id.startswith("Lidar") and env_id != "LidarLine" else 2.0) * 0.05
     assert (dmin > min_dist).all()
     if env_id.startswith("Lidar"):
         ob = _np_obstacles(g.env_states.obstacle)
-        assert not env_np.rect_inside(pos, ob, min_dist / 2).any()
+        assert not env_np.rect_inside(pos, ob, 0.05 if env_id == "LidarLine" else min_dist / 2).any()
     else:
         ob = None
     action = torch.rand((10, n, 2), device="cuda") * 2.4 - 1.2
@@ -107,7 +110,7 @@ def test_env_api_reset_step(env_id, n, obs):
     g1 = env.reset(3)
     assert g1.is_single and g1.nodes.shape == (cfg.n_nodes, cfg.node_dim)
     r1 = env.step(g1, action[0])
-    assert r1.graph.is_single and r1.reward.shape == () and r1.cost.shape == (n, 2)
+    assert r1.graph.is_single and r1.reward.shape == () and r1.cost.shape == (n, cfg.n_cost)
 
 
 def test_algo_api_act_step_collect_update():
@@ -146,8 +149,8 @@ def test_algo_api_act_step_collect_update():
     assert torch.equal(ro.graph.nodes[:, 1:], ro.next_graph.nodes[:, :-1])      # next_graph[t] == graph[t+1]
     assert (ro.rnn_states[:, 0] == 0).all()
     # update pre-pass: Vh, GAE, advantage against the oracle
-    info = algo.update(ro, step=0)
-    pp = algo.last_prepass
+    pp = algo.prepass(ro, step=0)          # (update() = this pre-pass + the PPO minibatch scan, which moves the weights)
+    info = {"eval/safe_data": float(pp["bTa_is_safe"].float().mean())}
     Vh, Vl, Qh, Ql, A = (pp[k].cpu().numpy() for k in ("bTp1ah_Vh", "bTp1_Vl", "bTah_Qh", "bT_Ql", "bTa_A"))
     assert Vh.shape == (b, T + 1, n, 2) and Vl.shape == (b, T + 1) and A.shape == (b, T, n)
     gt = {k: getattr(ro.graph, k)[:, 5].cpu().numpy() for k in G.GRAPH_FIELDS}

@@ -116,3 +116,84 @@ def test_collect_raises_for_infeasible_area():
     algo2 = make_algo("dgppo", env=env2, node_dim=7, edge_dim=4, state_dim=4, action_dim=2, n_agents=3, batch_size=4)
     ro = algo2.collect(algo2.params, np.arange(4, dtype=np.uint64))
     assert ro.actions.shape == (4, 2, 3, 2)
+
+
+LANDMARK_CASES = {
+    "LidarLine": env_np.EnvCfg(env_np.LIDAR_LINE, n=4, n_obs=3),
+    "LidarLine_n7": env_np.EnvCfg(env_np.LIDAR_LINE, n=7, n_obs=4),
+    "MPELine_n3": env_np.EnvCfg(env_np.MPE_LINE, n=3, n_obs=3),
+    "MPELine_n5": env_np.EnvCfg(env_np.MPE_LINE, n=5, n_obs=3),
+    "MPEFormation": env_np.EnvCfg(env_np.MPE_FORMATION, n=4, n_obs=3),
+    "MPEConnectSpread": env_np.EnvCfg(env_np.MPE_CONNECT_SPREAD, n=3, n_obs=1, area=1.0, obs_radius=0.25),
+}
+
+
+def _run_landmark(cfg, keys):
+    b = len(keys)
+    k = torch.from_numpy(np.asarray(keys, np.uint64).astype(np.int64)).cuda()
+    agent = torch.empty((b, cfg.n, 4), device="cuda")
+    goal = torch.empty((b, cfg.n_goal, 4), device="cuda")
+    w = _lib.OBS_STRIDE if cfg.is_lidar else 4
+    obst = torch.empty((b, cfg.n_obs, w), device="cuda")
+    nd = torch.empty(b, dtype=torch.int32, device="cuda")
+    cc = util.c_cfg(cfg)
+    rc = _lib.lib().dgppo_reset(util.stream(), C.byref(cc), util.p(k), 0.1, 0.3, 0.0, np.pi, util.p(agent),
+                                util.p(goal), util.p(obst), util.p(nd), b)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return agent.cpu().numpy(), goal.cpu().numpy(), obst.cpu().numpy(), nd.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(LANDMARK_CASES))
+def test_landmark_reset_matches_oracle(name):
+    """Line / Formation / ConnectSpread samplers (lidar_line.py:38-126, mpe_line.py:38-117,
+    mpe_formation.py:38-91, mpe_connect_spread.py:52-103) against their restatement, same counter stream."""
+    cfg = LANDMARK_CASES[name]
+    keys = np.array([0, 1, 2, 12345, 2 ** 40 + 7, 2 ** 63 + 11], np.uint64)
+    agent, goal, obst, nd = _run_landmark(cfg, keys)
+    for i, key in enumerate(keys):
+        ra, rg, ro, rn = reset_np.reset_landmark_states(cfg, int(key))
+        assert nd[i] == rn, f"{name} key {key}: number of draws"
+        np.testing.assert_array_equal(agent[i], ra)
+        np.testing.assert_array_equal(goal[i], rg)
+        if cfg.is_lidar:
+            np.testing.assert_array_equal(obst[i][:, :5], ro[:, :5])
+            np.testing.assert_allclose(obst[i][:, 5:], ro[:, 5:], rtol=1e-6, atol=1e-6)     # libm cos / sin
+        else:
+            np.testing.assert_array_equal(obst[i], ro)
+
+
+@pytest.mark.parametrize("name", list(LANDMARK_CASES))
+def test_landmark_reset_invariants(name):
+    cfg = LANDMARK_CASES[name]
+    keys = np.arange(256, dtype=np.uint64) * 7919 + 3
+    agent, goal, obst, nd = _run_landmark(cfg, keys)
+    assert (nd > 0).all()
+    pos = agent[..., :2]
+    n = cfg.n
+    dmin = (np.linalg.norm(pos[:, :, None] - pos[:, None], axis=-1) + np.eye(n) * 10).min(-1)
+    assert (dmin > (2.3 if cfg.kind == env_np.MPE_CONNECT_SPREAD else 2.0) * cfg.car_radius).all()
+    assert (pos >= 0).all() and (pos[..., 0] <= cfg.area).all()
+    if cfg.kind == env_np.MPE_CONNECT_SPREAD:
+        assert (dmin <= cfg.connect_radius).all()                                    # agents connected
+        g = goal[..., :2]
+        gmin = (np.linalg.norm(g[:, :, None] - g[:, None], axis=-1) + np.eye(n) * 10).min(-1)
+        assert (gmin <= cfg.connect_radius).all()
+        assert (obst[:, 0, 1] == np.float32(cfg.area / 2)).all()
+        assert (g[..., 1] > pos[..., 1].max()).all() or (g[..., 1].min() > cfg.area / 2)   # goals past the obstacle
+    else:
+        eg = env_np.landmark2goal(cfg, goal[..., :2])
+        if cfg.kind in (env_np.LIDAR_LINE, env_np.MPE_LINE):
+            short = cfg.kind == env_np.MPE_LINE and n <= 3
+            lm_min = n * 5 * cfg.car_radius if short else (n - 2) * 6 * cfg.car_radius
+            assert (np.linalg.norm(goal[:, 1, :2] - goal[:, 0, :2], axis=-1) >= np.float32(lm_min) - 1e-6).all()
+        if cfg.is_lidar:
+            th = obst[..., 4]
+            ob = dict(center=obst[..., 0:2], width=obst[..., 2], height=obst[..., 3], cos=obst[..., 5], sin=obst[..., 6])
+            pts = np.concatenate([pos, eg], axis=1)
+            assert not env_np.rect_inside(pts, ob, np.float32(cfg.car_radius) * np.float32(1.1)).any()
+            assert (th >= 0).all() and (th <= np.pi + 1e-6).all()
+        else:
+            d_a = np.linalg.norm(pos[:, :, None] - obst[:, None, :, :2], axis=-1)
+            d_g = np.linalg.norm(eg[:, :, None] - obst[:, None, :, :2], axis=-1)
+            assert (d_a > cfg.car_radius + cfg.obs_radius).all() and (d_g > 2 * cfg.car_radius + cfg.obs_radius).all()

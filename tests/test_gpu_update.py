@@ -76,3 +76,33 @@ def test_update_rejects_inconsistent_sizes():
     ro = algo.collect(algo.params, np.arange(32))
     with pytest.raises(ValueError):
         algo.update(ro, 0)
+
+
+@pytest.mark.parametrize("env_id,n,obs", [("MPEConnectSpread", 3, 1), ("LidarLine", 4, 3), ("MPEFormation", 4, 2)])
+def test_collect_and_update_on_widened_families(env_id, n, obs):
+    """Rollout + update through a three-cost env (Vh with 3 outputs, GAE with nh = 3) and through the landmark
+    families (goal nodes != agents): shapes, finiteness, the record's graph equals a fresh get_graph."""
+    from dgppo_b200.algo import make_algo
+    from dgppo_b200.env import make_env
+    T = 32
+    env = make_env(env_id, num_agents=n, num_obs=obs, max_step=T)
+    algo = make_algo("dgppo", env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
+                     action_dim=env.action_dim, n_agents=n, batch_size=512, rnn_step=16, seed=1)
+    ro = algo.collect(algo.params, np.arange(16) + 3)
+    assert ro.costs.shape == (16, T, n, env.n_cost)
+    d = env.graph_dims()
+    assert ro.graph.nodes.shape == (16, T, d.n_nodes, d.node_dim)
+    assert ro.graph.env_states.goal.shape[-2] == env.num_goals
+    # slot t of the record == get_graph of the state stored there
+    es0 = ro.graph.env_states                      # agent / goal are per slot, the obstacles static per env
+    es = type(es0)(es0.agent[:, 7], es0.goal[:, 7], es0[2])
+    if env_id.startswith("Lidar"):
+        hits = ro.graph.states[:, 7, n + env.num_goals:n + env.num_goals + 8 * n, :2].reshape(16, n, 8, 2)
+        g7 = env.get_graph(es, hits)
+    else:
+        g7 = env.get_graph(es)
+    for k in ("nodes", "edges", "receivers", "senders"):
+        assert torch.equal(getattr(g7, k), getattr(ro.graph, k)[:, 7]), k
+    info = algo.update(ro, 0)
+    assert all(np.isfinite(v) for v in info.values()), info
+    assert algo.last_prepass["bTp1ah_Vh"].shape == (16, T + 1, n, env.n_cost)

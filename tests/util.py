@@ -31,9 +31,19 @@ CONFIGS = {   # BASELINE.json configs at test sizes (b small), + edge cases
 }
 
 
+_TABLES = {}      # device goal tables stay alive for the test session
+
+
 def c_cfg(cfg: env_np.EnvCfg) -> _lib.DgppoEnvCfg:
+    table = None
+    if cfg.kind == env_np.MPE_FORMATION:
+        key = (cfg.n, cfg.comm_radius)
+        if key not in _TABLES:
+            _TABLES[key] = torch.as_tensor(env_np.formation_offsets(cfg)).cuda().contiguous()
+        table = _TABLES[key].data_ptr()
     return _lib.DgppoEnvCfg(cfg.kind, cfg.n, cfg.n_obs, cfg.n_rays, cfg.top_k, 0, cfg.comm_radius,
-                            cfg.car_radius, cfg.obs_radius, cfg.area, cfg.dt, cfg.dist2goal)
+                            cfg.car_radius, cfg.obs_radius, cfg.area, cfg.dt, cfg.dist2goal,
+                            cfg.connect_radius, table)
 
 
 def obs_record(obs: dict) -> np.ndarray:
@@ -68,7 +78,7 @@ def k_env_step(cfg, agent, goal, obs_nodes, action):
     a, g, o, u = dev(agent), dev(goal), dev(obs_nodes), dev(action)
     nxt = torch.empty_like(a)
     rew = torch.empty(b, device="cuda")
-    cost = torch.empty((b, n, 2), device="cuda")
+    cost = torch.empty((b, n, cfg.n_cost), device="cuda")
     cc = c_cfg(cfg)
     _lib.check(_lib.lib().dgppo_env_step(stream(), C.byref(cc), p(a), p(g), p(o), p(u), p(nxt), p(rew), p(cost), 1, b),
                "env_step")

@@ -23,12 +23,16 @@ if os.environ.get("FORCE_SAFE") == "1":       # plain PPO on the reward: A = -no
         sgn = float(os.environ.get("A_SIGN", "-1")); return (sgn * Al)[:, :, None].expand_as(A).contiguous(), deriv, acbf, torch.ones_like(safe)
     algo.cbf_advantage = patched
 rng = np.random.default_rng(0)
+WARM = int(os.environ.get("WARM", "0"))
+PRINT = int(os.environ.get("PRINT", "4"))
 for step in range(int(os.environ.get("STEPS", "40"))):
+    if WARM:
+        algo._train_state("policy")["opt"].lr = 0.0 if step < WARM else algo._lrs["policy"]
     keys = rng.integers(0, 2**31 - 1, size=128)
     ro = algo.collect(algo.params, keys)
     info = algo.update(ro, step)
     pp = algo.last_prepass
-    if step % 4 == 0:
+    if step % PRINT == 0:
         c = ro.costs
         A = pp["bTa_A"]
         print(f"step {step}: reward {float(ro.rewards.sum(1).mean()):.3f} cost>0 {float((c > 0).float().mean()):.3f} "

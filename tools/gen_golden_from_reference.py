@@ -33,6 +33,11 @@ CASES = {   # name -> (module, class, n_agents, n_obs, n_envs, n_steps)
     "LidarSpread_n4_obs0": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 4, 0, 3, 4),
     "MPETarget_n6_obs3": ("dgppo.env.mpe.mpe_target", "MPETarget", 6, 3, 4, 5),
     "MPECorridor_n5_obs2": ("dgppo.env.mpe.mpe_corridor", "MPECorridor", 5, 2, 4, 5),
+    "LidarLine_n4_obs3": ("dgppo.env.lidar_env.lidar_line", "LidarLine", 4, 3, 4, 5),
+    "MPELine_n3_obs3": ("dgppo.env.mpe.mpe_line", "MPELine", 3, 3, 4, 5),
+    "MPELine_n5_obs3": ("dgppo.env.mpe.mpe_line", "MPELine", 5, 3, 4, 5),
+    "MPEFormation_n4_obs3": ("dgppo.env.mpe.mpe_formation", "MPEFormation", 4, 3, 4, 5),
+    "MPEConnectSpread_n3_obs1": ("dgppo.env.mpe.mpe_connect_spread", "MPEConnectSpread", 3, 1, 4, 5),
 }
 GRAPH_FIELDS = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
 
