@@ -41,7 +41,7 @@ class DgppoNetLayout(C.Structure):
                                           "tc_head", "total")])
 
 
-ABI_VERSION = 6        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
+ABI_VERSION = 7        # DGPPO_ABI_VERSION of include/dgppo_abi.h this mirror was written against
 
 _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 
@@ -50,6 +50,10 @@ class DgppoRolloutBuffers(C.Structure):
     _fields_ = [(k, _fp) for k in ("nodes", "edges", "states", "receivers", "senders", "node_type",
                                    "n_node", "n_edge", "rnn", "eps", "actions", "log_pis", "rewards",
                                    "costs", "agent_ws", "hits_ws", "goal", "obstacles", "ray_dirs", "hits_ws2")]
+
+
+class DgppoStateRecord(C.Structure):
+    _fields_ = [(k, _fp) for k in ("agent", "obs_nodes", "goal")]
 
 
 NET_POLICY, NET_VH, NET_VL = 0, 1, 2
@@ -79,6 +83,16 @@ SIGNATURES = {
     "dgppo_vl_scan": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
                                 _fp, _fp, _fp, _fp, C.c_int32,
                                 _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32]),
+    "dgppo_gnn_policy_from_state": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
+                                              C.POINTER(DgppoStateRecord), C.c_int32,
+                                              _fp, _fp, C.c_int32, _fp, C.c_int32,
+                                              _fp, _fp, C.c_int32, C.c_int32]),
+    "dgppo_gnn_value_from_state": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
+                                             C.POINTER(DgppoStateRecord), C.c_int32,
+                                             _fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32]),
+    "dgppo_vl_scan_from_state": (C.c_int, [_fp, C.POINTER(DgppoEnvCfg), C.POINTER(DgppoNetCfg), _fp,
+                                           C.POINTER(DgppoStateRecord), C.c_int32,
+                                           _fp, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32]),
     "dgppo_gae": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, _fp, _fp,
                             C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dgppo_cbf_advantage": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float,

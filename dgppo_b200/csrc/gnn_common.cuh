@@ -31,7 +31,80 @@ struct GnnArgs {
   float* value; int out_pitch;
   int n_graphs;                 // b * n_slots
   int n, N, E, nd, n_ag, n_ao, G;
+  // "graph from state" mode (c_agent != nullptr): nodes / edges / recv / send are not read; the tile's node
+  // features, slot masks and edge features are formed from K3's INPUTS with K3's arithmetic (csrc/env_kernels.cu
+  // build_graph_kernel), so the policy sees bit for bit the graph K3 would have written to the record.
+  const float* c_agent;         // (b, c_pitch, n, sd) slot pointer
+  const float* c_obs;           // Lidar: hits (b, c_pitch, n, top_k, 2) slot pointer; MPE: obstacles (b, n_obs, 4), static
+  const float* c_goal;          // (b, g, sd), static per env
+  int c_pitch, g_nodes, sd, c_lidar, c_paired;
+  float cR, cR_diag, cR_obs, cR_mpe_obs;
 };
+
+// one node row of a graph in the layout of the x0 tile ([state | one-hot(obstacle, goal, agent)], stride X0S),
+// from the state arrays (lidar_env/base.py:234-264, mpe/base.py:214-233); row in [0, N - 1)
+__device__ __forceinline__ void node_row_from_state(const GnnArgs& g, int env, int slot, int row, float* dst) {
+  const int n = g.n, gn = g.g_nodes, sd = g.sd;
+  float v[X0S];
+#pragma unroll
+  for (int c = 0; c < X0S; ++c) v[c] = 0.f;
+  if (row < n) {
+    const float* s = g.c_agent + (((size_t)env * g.c_pitch + slot) * n + row) * sd;
+    for (int c = 0; c < sd; ++c) v[c] = __ldg(s + c);
+    v[sd + 2] = 1.f;
+  } else if (row < n + gn) {
+    const float* s = g.c_goal + ((size_t)env * gn + (row - n)) * sd;
+    for (int c = 0; c < sd; ++c) v[c] = __ldg(s + c);
+    v[sd + 1] = 1.f;
+  } else {
+    const int o = row - n - gn;
+    if (g.c_lidar) {
+      const float* s = g.c_obs + (((size_t)env * g.c_pitch + slot) * (size_t)(g.N - 1 - n - gn) + o) * 2;
+      v[0] = __ldg(s); v[1] = __ldg(s + 1);
+    } else {
+      const float* s = g.c_obs + ((size_t)env * (g.N - 1 - n - gn) + o) * 4;
+      for (int c = 0; c < 4; ++c) v[c] = __ldg(s + c);
+    }
+    v[sd] = 1.f;
+  }
+#pragma unroll
+  for (int c = 0; c < X0S; ++c) dst[c] = v[c];
+}
+
+// state2feat of a staged node row (identity, or [x, y, v cos, v sin] for the bicycle: lidar_bicycle_target.py:113-118)
+__device__ __forceinline__ float4 feat_of_row(const float* x, bool bic) {
+  return bic ? make_float4(x[0], x[1], fmul(x[4], x[2]), fmul(x[4], x[3])) : make_float4(x[0], x[1], x[2], x[3]);
+}
+// slot t of receiver agent i: sender node (graph-local) and whether the slot is live
+// (lidar_spread.py:57-96, lidar_target.py:57-96, mpe_spread.py:51-81; K3's edge loop)
+__device__ __forceinline__ int slot_sender_from_state(const GnnArgs& g, const float* xg /* the graph's x0 rows */,
+                                                      int i, int t, bool& live) {
+  const int n = g.n;
+  const float* a = xg + i * X0S;
+  if (t < n) {
+    const float* c = xg + t * X0S;
+    float dist = norm2(fsub(a[0], c[0]), fsub(a[1], c[1]));
+    dist = fadd(dist, (i == t) ? g.cR_diag : 0.f);
+    live = dist < g.cR;
+    return t;
+  }
+  if (t < n + g.n_ag) {
+    live = true;
+    return g.c_paired ? n + i : n + (t - n);
+  }
+  const int q = t - n - g.n_ag;
+  const int s = n + g.g_nodes + (g.c_lidar ? i * g.n_ao + q : q);
+  const float* c = xg + s * X0S;
+  live = norm2(fsub(a[0], c[0]), fsub(a[1], c[1])) < (g.c_lidar ? g.cR_obs : g.cR_mpe_obs);
+  return s;
+}
+// edge feature of slot t (receiver row a, sender row c of the x0 tile), K3's expressions
+__device__ __forceinline__ float4 edge_from_state(const GnnArgs& g, const float* a, const float* c, int t) {
+  if (t >= g.n + g.n_ag && g.c_lidar) return make_float4(fsub(a[0], c[0]), fsub(a[1], c[1]), 0.f, 0.f);
+  const bool bic = g.sd == 5;
+  const float4 fa = feat_of_row(a, bic), fc = feat_of_row(c, bic && t < g.n + g.n_ag);
+  return make_float4(fsub(fa.x, fc.x), fsub(fa.y, fc.y), fsub(fa.z, fc.z), fsub(fa.w, fc.w));
+}
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 

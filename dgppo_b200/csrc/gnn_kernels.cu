@@ -489,6 +489,14 @@ static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* n
   if (d.n > R) return DGPPO_ENOTSUP;
   if (g.n_graphs == 0) return 0;
   g.n = d.n; g.N = d.N; g.E = d.E; g.nd = d.nd; g.n_ag = d.n_ag; g.n_ao = d.n_ao;
+  if (g.c_agent) {                                    // graph-from-state mode: K3's constants (env_kernels.cu make_consts)
+    g.g_nodes = d.g; g.sd = d.sd; g.c_lidar = is_lidar(env->kind) ? 1 : 0; g.c_paired = is_target(env->kind) ? 1 : 0;
+    g.cR = (float)env->comm_radius; g.cR_diag = (float)(env->comm_radius + 1.0);
+    g.cR_obs = (float)(env->comm_radius - 1e-1);
+    g.cR_mpe_obs = (float)(is_tall_mpe(env->kind) ? env->comm_radius * 100 : env->comm_radius);
+    if (d.n_on > 0 && !g.c_obs) return DGPPO_EINVAL;
+    if (!g.c_goal) return DGPPO_EINVAL;
+  }
   g.G = R / d.n;
   const int m_cap = g.G * (d.N - 1);
 
@@ -514,6 +522,7 @@ static int launch_gnn(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* n
     if (rc2 != DGPPO_V2_UNSUPPORTED) return rc2;
   }
   if (phase != 0) return DGPPO_V2_UNSUPPORTED;      // the fused fallback kernel cannot be split
+  if (g.c_agent) return DGPPO_ENOTSUP;              // ... nor build the graph from the state
 
   const size_t x0_fl = (size_t)m_cap * X0S > (size_t)HID * RS ? (size_t)m_cap * X0S : (size_t)HID * RS;
   const size_t fl = x0_fl + (net->n_layers == 2 ? (size_t)m_cap * X1S : 0) +
@@ -543,52 +552,60 @@ extern "C" int dgppo_net_layout(const DgppoNetCfg* net, DgppoNetLayout* out) {
   return fill_layout(net, out);
 }
 
-extern "C" int dgppo_gnn_policy(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
-                                const float* params, const float* nodes, const float* edges,
-                                const int32_t* receivers, const int32_t* senders, int32_t pitch,
-                                const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
-                                const float* eps, int32_t eps_pitch, float* action, float* log_pi,
-                                int32_t act_pitch, int32_t b) {
+static void set_graph_source(GnnArgs& g, const float* nodes, const float* edges, const int32_t* receivers,
+                             const int32_t* senders, const DgppoStateRecord* st, int32_t pitch) {
+  g.nodes = nodes; g.edges = edges; g.recv = receivers; g.send = senders; g.pitch = pitch;
+  g.c_agent = st ? st->agent : nullptr; g.c_obs = st ? st->obs_nodes : nullptr; g.c_goal = st ? st->goal : nullptr;
+  g.c_pitch = pitch;
+}
+
+static int policy_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net, const float* params,
+                       const float* nodes, const float* edges, const int32_t* receivers, const int32_t* senders,
+                       const DgppoStateRecord* st, int32_t pitch, const float* rnn_in, float* rnn_out,
+                       int32_t rnn_pitch, const float* eps, int32_t eps_pitch, float* action, float* log_pi,
+                       int32_t act_pitch, int32_t b) {
   if (!net || net->kind != DGPPO_NET_POLICY) return DGPPO_EINVAL;
-  if (b < 0 || !params || !nodes || !edges || !receivers || !senders || !rnn_in || !rnn_out || !action)
-    return DGPPO_EINVAL;
+  if (b < 0 || !params || !rnn_in || !rnn_out || !action) return DGPPO_EINVAL;
+  if (st ? !st->agent : (!nodes || !edges || !receivers || !senders)) return DGPPO_EINVAL;
   if (pitch < 1 || rnn_pitch < 1 || act_pitch < 1 || (eps && eps_pitch < 1)) return DGPPO_EINVAL;
   GnnArgs g{};
-  g.nodes = nodes; g.edges = edges; g.recv = receivers; g.send = senders; g.pitch = pitch; g.n_slots = 1;
+  set_graph_source(g, nodes, edges, receivers, senders, st, pitch);
+  g.n_slots = 1;
   g.rnn_in = rnn_in; g.rnn_out = rnn_out; g.rnn_pitch = rnn_pitch;
   g.eps = eps; g.eps_pitch = eps_pitch; g.action = action; g.log_pi = log_pi; g.act_pitch = act_pitch;
   g.value = nullptr; g.out_pitch = 1; g.n_graphs = b;
   return launch_gnn(stream, env, net, params, g);
 }
 
-extern "C" int dgppo_gnn_value(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
-                               const float* params, const float* nodes, const float* edges,
-                               const int32_t* receivers, const int32_t* senders, int32_t pitch,
-                               const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
-                               float* value, int32_t out_pitch, int32_t n_slots, int32_t b) {
+static int value_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net, const float* params,
+                      const float* nodes, const float* edges, const int32_t* receivers, const int32_t* senders,
+                      const DgppoStateRecord* st, int32_t pitch, const float* rnn_in, float* rnn_out,
+                      int32_t rnn_pitch, float* value, int32_t out_pitch, int32_t n_slots, int32_t b) {
   if (!net || net->kind == DGPPO_NET_POLICY) return DGPPO_EINVAL;
-  if (b < 0 || !params || !nodes || !edges || !receivers || !senders || !rnn_in || !value) return DGPPO_EINVAL;
+  if (b < 0 || !params || !rnn_in || !value) return DGPPO_EINVAL;
+  if (st ? !st->agent : (!nodes || !edges || !receivers || !senders)) return DGPPO_EINVAL;
   if (pitch < 1 || rnn_pitch < 1 || out_pitch < 1 || n_slots < 1 || n_slots > pitch) return DGPPO_EINVAL;
   GnnArgs g{};
-  g.nodes = nodes; g.edges = edges; g.recv = receivers; g.send = senders; g.pitch = pitch; g.n_slots = n_slots;
+  set_graph_source(g, nodes, edges, receivers, senders, st, pitch);
+  g.n_slots = n_slots;
   g.rnn_in = rnn_in; g.rnn_out = rnn_out; g.rnn_pitch = rnn_pitch;
   g.eps = nullptr; g.eps_pitch = 1; g.action = nullptr; g.log_pi = nullptr; g.act_pitch = 1;
   g.value = value; g.out_pitch = out_pitch; g.n_graphs = b * n_slots;
   return launch_gnn(stream, env, net, params, g);
 }
 
-extern "C" int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
-                             const float* params, const float* nodes, const float* edges,
-                             const int32_t* receivers, const int32_t* senders, int32_t pitch,
-                             float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
-                             int32_t n_slots, int32_t b) {
+static int vl_scan_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net, const float* params,
+                        const float* nodes, const float* edges, const int32_t* receivers, const int32_t* senders,
+                        const DgppoStateRecord* st, int32_t pitch, float* carry, int32_t carry_pitch, float* value,
+                        int32_t out_pitch, int32_t n_slots, int32_t b) {
   if (!net || net->kind != DGPPO_NET_VL) return DGPPO_EINVAL;
-  if (b < 0 || !params || !nodes || !edges || !receivers || !senders || !carry || !value) return DGPPO_EINVAL;
+  if (b < 0 || !params || !carry || !value) return DGPPO_EINVAL;
+  if (st ? !st->agent : (!nodes || !edges || !receivers || !senders)) return DGPPO_EINVAL;
   if (pitch < 1 || out_pitch < 1 || n_slots < 1 || n_slots > pitch || n_slots > out_pitch ||
       carry_pitch < n_slots + 1) return DGPPO_EINVAL;
   if (b == 0) return 0;
   GnnArgs g{};
-  g.nodes = nodes; g.edges = edges; g.recv = receivers; g.send = senders; g.pitch = pitch;
+  set_graph_source(g, nodes, edges, receivers, senders, st, pitch);
   g.eps = nullptr; g.eps_pitch = 1; g.action = nullptr; g.log_pi = nullptr; g.act_pitch = 1;
   g.rnn_pitch = carry_pitch; g.out_pitch = out_pitch;
   // phase 1: the GNN part of every slot has no recurrence: one launch over all b * n_slots graphs,
@@ -597,11 +614,13 @@ extern "C" int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNe
   g.rnn_in = carry; g.rnn_out = carry + HID; g.value = value;
   int rc = launch_gnn(stream, env, net, params, g, 1);
   if (rc == DGPPO_V2_UNSUPPORTED) {                   // shape outside the split kernels: slot by slot
+    if (st) return DGPPO_ENOTSUP;
+    const GraphDims d = graph_dims(*env);
     for (int t = 0; t < n_slots; ++t) {
       GnnArgs s = g;
-      s.nodes = nodes + (size_t)t * graph_dims(*env).N * graph_dims(*env).nd;
-      s.edges = edges + (size_t)t * graph_dims(*env).E * 4;
-      s.recv = receivers + (size_t)t * graph_dims(*env).E; s.send = senders + (size_t)t * graph_dims(*env).E;
+      s.nodes = nodes + (size_t)t * d.N * d.nd;
+      s.edges = edges + (size_t)t * d.E * 4;
+      s.recv = receivers + (size_t)t * d.E; s.send = senders + (size_t)t * d.E;
       s.n_slots = 1; s.n_graphs = b;
       s.rnn_in = carry + (size_t)t * HID; s.rnn_out = carry + (size_t)(t + 1) * HID; s.value = value + t;
       if ((rc = launch_gnn(stream, env, net, params, s, 0))) return rc;
@@ -617,4 +636,60 @@ extern "C" int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNe
     if ((rc = launch_gnn(stream, env, net, params, s, 2))) return rc;
   }
   return 0;
+}
+
+extern "C" int dgppo_gnn_policy(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                                const float* params, const float* nodes, const float* edges,
+                                const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                                const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                                const float* eps, int32_t eps_pitch, float* action, float* log_pi,
+                                int32_t act_pitch, int32_t b) {
+  return policy_impl(stream, env, net, params, nodes, edges, receivers, senders, nullptr, pitch, rnn_in, rnn_out,
+                     rnn_pitch, eps, eps_pitch, action, log_pi, act_pitch, b);
+}
+
+extern "C" int dgppo_gnn_policy_from_state(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                                           const float* params, const DgppoStateRecord* st, int32_t pitch,
+                                           const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                                           const float* eps, int32_t eps_pitch, float* action, float* log_pi,
+                                           int32_t act_pitch, int32_t b) {
+  if (!st) return DGPPO_EINVAL;
+  return policy_impl(stream, env, net, params, nullptr, nullptr, nullptr, nullptr, st, pitch, rnn_in, rnn_out,
+                     rnn_pitch, eps, eps_pitch, action, log_pi, act_pitch, b);
+}
+
+extern "C" int dgppo_gnn_value(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                               const float* params, const float* nodes, const float* edges,
+                               const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                               const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                               float* value, int32_t out_pitch, int32_t n_slots, int32_t b) {
+  return value_impl(stream, env, net, params, nodes, edges, receivers, senders, nullptr, pitch, rnn_in, rnn_out,
+                    rnn_pitch, value, out_pitch, n_slots, b);
+}
+
+extern "C" int dgppo_gnn_value_from_state(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                                          const float* params, const DgppoStateRecord* st, int32_t pitch,
+                                          const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                                          float* value, int32_t out_pitch, int32_t n_slots, int32_t b) {
+  if (!st) return DGPPO_EINVAL;
+  return value_impl(stream, env, net, params, nullptr, nullptr, nullptr, nullptr, st, pitch, rnn_in, rnn_out,
+                    rnn_pitch, value, out_pitch, n_slots, b);
+}
+
+extern "C" int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                             const float* params, const float* nodes, const float* edges,
+                             const int32_t* receivers, const int32_t* senders, int32_t pitch,
+                             float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
+                             int32_t n_slots, int32_t b) {
+  return vl_scan_impl(stream, env, net, params, nodes, edges, receivers, senders, nullptr, pitch, carry, carry_pitch,
+                      value, out_pitch, n_slots, b);
+}
+
+extern "C" int dgppo_vl_scan_from_state(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                                        const float* params, const DgppoStateRecord* st, int32_t pitch,
+                                        float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
+                                        int32_t n_slots, int32_t b) {
+  if (!st) return DGPPO_EINVAL;
+  return vl_scan_impl(stream, env, net, params, nullptr, nullptr, nullptr, nullptr, st, pitch, carry, carry_pitch,
+                      value, out_pitch, n_slots, b);
 }

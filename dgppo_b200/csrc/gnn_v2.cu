@@ -145,7 +145,8 @@ template <int INX, int J>
 __device__ __forceinline__ void attention_row(int r, bool live, int lane, const int* srow, int deg,
                                               const float* qrow /* qt + r*H*QTS */, int IN, float isd,
                                               const float* X, int XS, const float4* ed, int i_agent,
-                                              int n, int n_ag, int n_ao, float* scr, float* z) {
+                                              int n, int n_ag, int n_ao, float* scr, float* z,
+                                              const GnnArgs* cg = nullptr, const float* x0g = nullptr, int node0 = 0) {
   const int INA = IN + 5;
   float* zc = z + r;
   if (!live) {                                   // rows past the tile's graphs: zero column
@@ -184,7 +185,8 @@ __device__ __forceinline__ void attention_row(int r, bool live, int lane, const 
       const int e = (t < n) ? i_agent * n + t
                             : ((t < n + n_ag) ? n * n + i_agent * n_ag + (t - n)
                                               : n * n + n * n_ag + i_agent * n_ao + (t - n - n_ag));
-      ef[j] = __ldg(ed + e);
+      // edge features: from the record, or (graph-from-state mode) from the staged node rows with K3's arithmetic
+      ef[j] = cg ? edge_from_state(*cg, x0g + i_agent * X0S, x0g + (sv[j] - node0) * X0S, t) : __ldg(ed + e);
     }
   }
   {                                               // jraph.segment_softmax over the row's slots;
@@ -322,11 +324,38 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
         const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
         tab[64 + r] = env * g.pitch + slot;
         tab[96 + r] = env * g.rnn_pitch + slot;
+        tab[64 + R2 + r] = env;                      // graph-from-state mode: (env, slot) of the tile's graphs
+        tab[96 + R2 + r] = slot;
       }
     }
     for (int i = threadIdx.x; i < (M + 3) / 4; i += nth) reinterpret_cast<int*>(nflag)[i] = 0;
     __syncthreads();
 
+    const bool from_state = g.c_agent != nullptr;
+    if (from_state) {
+      // ---- graph from state: node rows with K3's layout, then slot masks / senders from the staged rows
+      for (int idx = threadIdx.x; idx < gcount * nodes_per; idx += nth) {
+        const int gl = idx / nodes_per, row = idx - gl * nodes_per;
+        node_row_from_state(g, tab[64 + R2 + gl], tab[96 + R2 + gl], row, x0 + (size_t)idx * X0S);
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < R2 * degp; idx += nth) {
+        const int r = idx >> dshift, t = idx & (degp - 1);
+        int s = -1;
+        const int gl = tab[r];
+        if (gl >= 0 && t < deg) {
+          bool live;
+          const int sd = slot_sender_from_state(g, x0 + (size_t)gl * nodes_per * X0S, tab[32 + r], t, live);
+          if (live) { s = gl * nodes_per + sd; nflag[s] = 1; }
+        }
+        sidx[idx] = s;
+      }
+      for (int idx = threadIdx.x; idx < 32 * R2; idx += nth) {       // layer 0: xr[c][r] = node row of agent(r)
+        const int c = idx / R2, r = idx % R2;
+        const int gl = tab[r];
+        xr[c * RS2 + r] = (gl >= 0 && c < net.L[0].in) ? x0[((size_t)gl * nodes_per + tab[32 + r]) * X0S + c] : 0.f;
+      }
+    } else {
     // ---- stage node features (async) and the per-row sender table
     for (int gl = 0; gl < gcount; ++gl) {
       const float* src = g.nodes + (size_t)tab[64 + gl] * N * nd;
@@ -368,6 +397,7 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
       xr[c * RS2 + r] = v;
     }
     cp_async_wait_all();
+    }
     __syncthreads();
 
     const float* X = x0; int XS = X0S;
@@ -399,16 +429,19 @@ gnn_layers_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict__ p
           const bool live = gl >= 0;
           const int ia = tab[32 + r];
           const float4* ed = reinterpret_cast<const float4*>(g.edges + (size_t)tab[64 + (live ? gl : 0)] * g.E * 4);
+          const GnnArgs* cgp = from_state ? &g : nullptr;
+          const int node0 = (live ? gl : 0) * nodes_per;
+          const float* x0g = x0 + (size_t)node0 * X0S;
           if (l == 0) {
             if (degp == 32) attention_row<X0S, 1>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
-                                                  X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+                                                  X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z, cgp, x0g, node0);
             else            attention_row<X0S, 2>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
-                                                  X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+                                                  X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z, cgp, x0g, node0);
           } else {
             if (degp == 32) attention_row<32, 1>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
-                                                 X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+                                                 X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z, cgp, x0g, node0);
             else            attention_row<32, 2>(r, live, lane, sidx + r * degp, deg, qt + r * H * QTS, IN, isd,
-                                                 X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z);
+                                                 X, XS, ed, ia, n, g.n_ag, g.n_ao, my_scr, z, cgp, x0g, node0);
           }
         }
       }
@@ -533,7 +566,8 @@ template <int INX>
 __device__ __forceinline__ void attention_row_big(int r, bool live, int lane, const unsigned short* srow, int deg, int degp,
                                                   const float* qrow, int IN, float isd,
                                                   const float* X, int XS, const float4* ed, int i_agent,
-                                                  int n, int n_ag, int n_ao, float4* al, float* z) {
+                                                  int n, int n_ag, int n_ao, float4* al, float* z,
+                                                  const GnnArgs* cg = nullptr, const float* x0g = nullptr) {
   const int INA = IN + 5;
   float* zc = z + r;
   if (!live) {
@@ -590,6 +624,8 @@ __device__ __forceinline__ void attention_row_big(int r, bool live, int lane, co
   auto edge_of = [&](int p) -> float4 {             // edge features of list entry p (global, L2)
     if (p >= count) return make_float4(0.f, 0.f, 0.f, 0.f);
     const int t = __float_as_int(al[p].w) >> 16;
+    if (cg)         // graph-from-state mode: K3's expressions on the staged node rows (al[p].w low half = sender * XS)
+      return edge_from_state(*cg, x0g + i_agent * X0S, x0g + ((__float_as_int(al[p].w) & 0xffff) / XS) * X0S, t);
     const int e = (t < n) ? i_agent * n + t
                           : ((t < n + n_ag) ? n * n + i_agent * n_ag + (t - n)
                                             : n * n + n * n_ag + i_agent * n_ao + (t - n - n_ag));
@@ -690,6 +726,22 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
     if (threadIdx.x < HID) vlsum[threadIdx.x] = 0.f;
     __syncthreads();
     const size_t gslot = (size_t)tab[64];
+    const bool from_state = g.c_agent != nullptr;
+    if (from_state) {
+      const int env = gi / g.n_slots, slot = gi - env * g.n_slots;
+      for (int row = threadIdx.x; row < M; row += nth) node_row_from_state(g, env, slot, row, x0 + (size_t)row * X0S);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < n * degp; idx += nth) {
+        const int i = idx / degp, t = idx - i * degp;
+        int s = 0xffff;
+        if (t < deg) {
+          bool live;
+          const int sd = slot_sender_from_state(g, x0, i, t, live);
+          if (live) { s = sd; if (NL > 1) nflag[sd] = 1; }
+        }
+        sidx[idx] = (unsigned short)s;
+      }
+    } else {
     {
       const float* src = g.nodes + gslot * N * nd;
       if (nd == X0S) {
@@ -702,7 +754,6 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
         for (int j = threadIdx.x; j < M; j += nth) x0[j * X0S + 7] = 0.f;
       }
     }
-    const float4* ed = reinterpret_cast<const float4*>(g.edges + gslot * g.E * 4);
     const int* recv = g.recv + gslot * g.E;
     const int* send = g.send + gslot * g.E;
     // ---- sender table of every receiver row, once per graph (loads are independent: no branch between them)
@@ -719,6 +770,9 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
       sidx[idx] = (unsigned short)s;
     }
     cp_async_wait_all();
+    }
+    const float4* ed = from_state ? nullptr : reinterpret_cast<const float4*>(g.edges + gslot * g.E * 4);
+    const GnnArgs* cgp = from_state ? &g : nullptr;
     __syncthreads();
 
     const float* X = x0; int XS = X0S;
@@ -750,9 +804,9 @@ gnn_layers_big_kernel(NetP net, GnnArgs g, GnnV2Plan pl, const float* __restrict
         __syncthreads();
         for (int r = warp; r < R2; r += nwarps) {
           if (l == 0) attention_row_big<X0S>(r, r < rows, lane, sidx + (a0 + r) * degp, deg, degp, qt + r * H * QTS, IN, isd,
-                                             X, XS, ed, a0 + r, n, g.n_ag, g.n_ao, my_al, z);
+                                             X, XS, ed, a0 + r, n, g.n_ag, g.n_ao, my_al, z, cgp, x0);
           else        attention_row_big<32>(r, r < rows, lane, sidx + (a0 + r) * degp, deg, degp, qt + r * H * QTS, IN, isd,
-                                            X, XS, ed, a0 + r, n, g.n_ag, g.n_ao, my_al, z);
+                                            X, XS, ed, a0 + r, n, g.n_ag, g.n_ao, my_al, z, cgp, x0);
         }
         __syncthreads();
         const int KZ = H * INA, kh = KZ / 2, hw = nwarps / 2;

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DGPPO_ABI_VERSION 6
+#define DGPPO_ABI_VERSION 7
 
 /* negative error codes (positive values are cudaError_t) */
 #define DGPPO_EINVAL   (-1)   /* inconsistent sizes / null pointer            */
@@ -300,6 +300,33 @@ int dgppo_vl_scan(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
                   const int32_t* receivers, const int32_t* senders, int32_t pitch,
                   float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
                   int32_t n_slots, int32_t b);
+
+/* ---- graph from state: the same three forwards WITHOUT a stored graph -------------------------------
+ * The compact Rollout record (dgppo/trainer/data.py:8-16) keeps K3's INPUTS per slot - agent
+ * states and LiDAR hit points - instead of the GraphsTuple arrays (2.9 KB instead of 10.7 KB per env-step at
+ * C3).  These entry points take that record: the GNN layers form node features, slot masks, senders and edge
+ * features of every graph in their staging phase with build_graph's own arithmetic
+ * (utils/graph.py:212-247 + each env's edge_blocks), so outputs equal the graph-record calls bit for bit.  */
+typedef struct DgppoStateRecord {
+  const float* agent;      /* (b, pitch, n, state_dim) slot pointer                                          */
+  const float* obs_nodes;  /* Lidar: hit points (b, pitch, n, top_k, 2) slot pointer; MPE: obstacle states
+                              (b, n_obs, 4), static per env; NULL iff n_obs == 0                              */
+  const float* goal;       /* (b, n_goals, state_dim), static per env                                        */
+} DgppoStateRecord;
+
+int dgppo_gnn_policy_from_state(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                                const float* params, const DgppoStateRecord* state, int32_t pitch,
+                                const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                                const float* eps, int32_t eps_pitch,
+                                float* action, float* log_pi, int32_t act_pitch, int32_t b);
+int dgppo_gnn_value_from_state(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                               const float* params, const DgppoStateRecord* state, int32_t pitch,
+                               const float* rnn_in, float* rnn_out, int32_t rnn_pitch,
+                               float* value, int32_t out_pitch, int32_t n_slots, int32_t b);
+int dgppo_vl_scan_from_state(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
+                             const float* params, const DgppoStateRecord* state, int32_t pitch,
+                             float* carry, int32_t carry_pitch, float* value, int32_t out_pitch,
+                             int32_t n_slots, int32_t b);
 
 /* ---- K5: GAE ---------------------------------------------------------------
  * compute_dec_ocp_gae (algo/utils.py:11-79; callers dgppo.py:232-237,268-273).

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libdgppo_b200.so does not export {s}"
     assert set(syms) == set(_lib.SIGNATURES), (set(syms) ^ set(_lib.SIGNATURES))
-    assert lib.dgppo_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.dgppo_abi_version() == _lib.ABI_VERSION == 7
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
