@@ -271,7 +271,8 @@ def measure(args, w, b, world, rank, local, full):
     h2d = agent_h.numel() * 4 + goal_h.numel() * 4 + obs_h.numel() * 4
     d2h = rew_h.numel() * 4 + cost_h.numel() * 4
 
-    record = RolloutRecord(env, b, T, dev, stochastic=True)
+    record = RolloutRecord(env, b, T, dev, stochastic=True, compact=args.record == "compact")
+    algo.compact_record = args.record == "compact"
     prof = _lib.lib().dgppo_prof_create(T)
 
     def reset_graph(agent_d, goal_d, obs_d):
@@ -493,6 +494,8 @@ def main():
     ap.add_argument("--scaling", type=str, default="strong", choices=["weak", "strong"],
                     help="strong (default): the workload's envs in total, sharded over the ranks; weak: per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--record", type=str, default=os.environ.get("DGPPO_BENCH_RECORD", "compact"), choices=["compact", "full"],
+                    help="rollout record: compact (K3's inputs per slot, graphs on demand) or full (GraphsTuple arrays)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -49,7 +49,8 @@ _fp = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
 class DgppoRolloutBuffers(C.Structure):
     _fields_ = [(k, _fp) for k in ("nodes", "edges", "states", "receivers", "senders", "node_type",
                                    "n_node", "n_edge", "rnn", "eps", "actions", "log_pis", "rewards",
-                                   "costs", "agent_ws", "hits_ws", "goal", "obstacles", "ray_dirs", "hits_ws2")]
+                                   "costs", "agent_ws", "hits_ws", "goal", "obstacles", "ray_dirs", "hits_ws2",
+                                   "agent_rec", "hits_rec")]
 
 
 class DgppoStateRecord(C.Structure):

@@ -28,7 +28,7 @@ from ..env.base import MultiAgentEnv, ptr, require_cuda, stream_ptr
 from ..env.envs import check_reset
 from ..trainer import distributed as D
 from ..trainer.data import Rollout
-from ..trainer.rollout import RNN_DIM, RolloutRecord, run_rollout, run_rollout_chunked
+from ..trainer.rollout import RNN_DIM, LazyGraphsTuple, RolloutRecord, run_rollout, run_rollout_chunked
 from ..utils.graph import GraphsTuple
 from . import params as P
 from . import update as U
@@ -99,6 +99,9 @@ class DGPPO(Algorithm):
         self.last_prepass: Optional[dict] = None
         self._workspaces: dict = {}
         # independent env groups run on separate streams so env kernels overlap policy kernels
+        # compact rollout records: K3's inputs per slot instead of the graph arrays; the value
+        # kernels and the update read them directly, GraphsTuple views are built on demand
+        self.compact_record = bool(kwargs.get("compact_record", os.environ.get("DGPPO_COMPACT", "0") == "1"))
         # (DGPPO_ROLLOUT_CHUNKS overrides; default by batch size, _n_chunks)
         self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "0"))
 
@@ -237,8 +240,9 @@ class DGPPO(Algorithm):
         if eps is None:
             eps = self._eps_from_key(b_key, (b, T, self.n_agents, self.action_dim))
         if record is None:       # one stochastic record per shape, reused: the returned Rollout aliases it (see _cached)
-            record = self._cached("record", self._shape_key(b),
-                                  lambda: RolloutRecord(self._env, b, T, graph0.nodes.device, stochastic=True))
+            record = self._cached("record", self._shape_key(b) + (self.compact_record,),
+                                  lambda: RolloutRecord(self._env, b, T, graph0.nodes.device, stochastic=True,
+                                                        compact=self.compact_record))
         ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, eps, T,
                                  self.init_rnn_state, record=record, n_chunks=self._n_chunks(b), prof=prof)
         if fresh:
@@ -251,9 +255,10 @@ class DGPPO(Algorithm):
         if fresh:
             graph0 = self._env.reset(b_key, defer_check=True)
         if record is None:       # update() calls this every step: keep one deterministic record instead of re-allocating GBs
-            record = self._cached("det_record", self._shape_key(graph0.nodes.shape[0]),
+            record = self._cached("det_record", self._shape_key(graph0.nodes.shape[0]) + (self.compact_record,),
                                   lambda: RolloutRecord(self._env, graph0.nodes.shape[0], self._env.max_episode_steps,
-                                                        graph0.nodes.device, stochastic=False))
+                                                        graph0.nodes.device, stochastic=False,
+                                                        compact=self.compact_record))
         ro = run_rollout_chunked(self._env, self.policy_cfg, self.packed("policy", params), graph0, None,
                                  self._env.max_episode_steps, self.init_rnn_state, record=record, test_mode=True,
                                  n_chunks=self._n_chunks(graph0.nodes.shape[0]))
@@ -262,12 +267,25 @@ class DGPPO(Algorithm):
         return ro
 
     @staticmethod
+    def _compact(rollout: Rollout):
+        """The compact record behind a Rollout, or None for a full (graph) record."""
+        g = rollout.graph
+        return g.record if isinstance(g, LazyGraphsTuple) else None
+
+    def _state_record(self, rec) -> "_lib.DgppoStateRecord":
+        obs = rec.hits_rec if rec.hits_rec is not None else rec._obstacles
+        return _lib.DgppoStateRecord(ptr(rec.agent_rec), ptr(obs), ptr(rec._goal))
+
+    @staticmethod
     def _record_arrays(rollout: Rollout):
         """(b, T+1, ...) graph arrays behind a Rollout: the shared record when the
         Rollout came from run_rollout (graph / next_graph are views of it), else a
         concatenation of graph and next_graph[:, -1]."""
         g, ng = rollout.graph, rollout.next_graph
         T = rollout.rewards.shape[1]
+        if isinstance(g, LazyGraphsTuple):          # compact record: build every graph (callers that can, avoid this)
+            m = g.record.materialize()
+            return [m[k] for k in ("nodes", "edges", "receivers", "senders")]
         out = []
         for name in ("nodes", "edges", "receivers", "senders"):
             a, an = getattr(g, name), getattr(ng, name)
@@ -285,22 +303,38 @@ class DGPPO(Algorithm):
         graphs of `rollout.graph` and `rollout.next_graph[:, -1]` are slots
         0..T of one record; the carry fed to the GRU is `rollout.rnn_states`
         for t < T and the policy's post-step carry for the final graph."""
-        g = rollout.graph
         b, T = rollout.rewards.shape
         n = self.n_agents
-        nodes, edges, recv, send = self._record_arrays(rollout)
+        crec = self._compact(rollout)
+        dev = rollout.rewards.device
         # carries: t < T as stored; final: act(next_graph[-1], rnn_states[-1]) -> its new carry
         rnn_rec = self._cached("vh_rnn_rec", self._shape_key(b),
-                               lambda: torch.empty((b, T + 1, n, RNN_DIM), dtype=torch.float32, device=nodes.device))
+                               lambda: torch.empty((b, T + 1, n, RNN_DIM), dtype=torch.float32, device=dev))
         rnn_rec[:, :T] = rollout.rnn_states.reshape(b, T, n, RNN_DIM)
-        last = GraphsTuple(*[t[:, -1] if isinstance(t, torch.Tensor) else None for t in rollout.next_graph])
-        _, _, final_carry = self._policy_call(last, rollout.rnn_states[:, -1].reshape(b, n, RNN_DIM), None, params)
-        rnn_rec[:, T] = final_carry
         nc = self._env.n_cost
-        Vh = torch.empty((b, T + 1, n, nc), dtype=torch.float32, device=nodes.device)
+        Vh = torch.empty((b, T + 1, n, nc), dtype=torch.float32, device=dev)
         # rnn_out: the kernels' scratch rows (the new carry is unused for Vh)
         scratch = self._cached("vh_scratch", self._shape_key(b), lambda: torch.empty_like(rnn_rec))
         cfg = self._env.env_cfg()
+        last_in = rollout.rnn_states[:, -1].reshape(b, n, RNN_DIM).contiguous()
+        if crec is not None:       # compact record: both forwards straight from the stored states
+            st_last = _lib.DgppoStateRecord(
+                ptr(crec.agent_rec[:, T]), ptr(crec.hits_rec[:, T] if crec.hits_rec is not None else crec._obstacles),
+                ptr(crec._goal))
+            act = torch.empty((b, n, self.action_dim), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().dgppo_gnn_policy_from_state(
+                stream_ptr(), C.byref(cfg), C.byref(self.policy_cfg), ptr(self.packed("policy", params)),
+                C.byref(st_last), T + 1, ptr(rnn_rec[:, T - 1]), ptr(rnn_rec[:, T]), T + 1, None, 1, ptr(act), None, 1, b),
+                "dgppo_gnn_policy_from_state")
+            st = self._state_record(crec)
+            _lib.check(_lib.lib().dgppo_gnn_value_from_state(
+                stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)), C.byref(st), T + 1,
+                ptr(rnn_rec), ptr(scratch), T + 1, ptr(Vh), T + 1, T + 1, b), "dgppo_gnn_value_from_state")
+            return Vh
+        nodes, edges, recv, send = self._record_arrays(rollout)
+        last = GraphsTuple(*[t[:, -1] if isinstance(t, torch.Tensor) else None for t in rollout.next_graph])
+        _, _, final_carry = self._policy_call(last, last_in, None, params)
+        rnn_rec[:, T] = final_carry
         _lib.check(_lib.lib().dgppo_gnn_value(
             stream_ptr(), C.byref(cfg), C.byref(self.Vh_cfg), ptr(self.packed("Vh", params)),
             ptr(nodes), ptr(edges), ptr(recv), ptr(send), T + 1, ptr(rnn_rec), ptr(scratch), T + 1,
@@ -330,15 +364,20 @@ class DGPPO(Algorithm):
         the centralised value is recurrent over T only through its GRU, so the
         GNN layers of all slots run at once and the head runs T+1 times
         (dgppo_vl_scan).  -> Vl (b, T+1), carries (b, T+1, 64)."""
-        g = rollout.graph
         b, T = rollout.rewards.shape
-        nodes, edges, recv, send = self._record_arrays(rollout)
-        d = self._env.graph_dims()
-        dev = nodes.device
+        dev = rollout.rewards.device
         carry = torch.zeros((b, T + 2, RNN_DIM), dtype=torch.float32, device=dev)
         carry[:, 0] = self.init_Vl_rnn_state.reshape(RNN_DIM)
         Vl = torch.empty((b, T + 1), dtype=torch.float32, device=dev)
         cfg, pv = self._env.env_cfg(), self.packed("Vl", params)
+        crec = self._compact(rollout)
+        if crec is not None:
+            st = self._state_record(crec)
+            _lib.check(_lib.lib().dgppo_vl_scan_from_state(
+                stream_ptr(), C.byref(cfg), C.byref(self.Vl_cfg), ptr(pv), C.byref(st), T + 1,
+                ptr(carry), T + 2, ptr(Vl), T + 1, T + 1, b), "dgppo_vl_scan_from_state")
+            return Vl, carry[:, :T + 1]
+        nodes, edges, recv, send = self._record_arrays(rollout)
         # one launch of the GNN layers over all b * (T + 1) graphs (no recurrence there), then the
         # GRU head slot by slot inside the library
         _lib.check(_lib.lib().dgppo_vl_scan(
@@ -425,7 +464,17 @@ class DGPPO(Algorithm):
         det = pp["det_rollout"]
         gi = U.GraphIndex(self.n_agents, self._env.graph_dims().n_ag, self._env.graph_dims().n_ao,
                           self._env.graph_dims().n_nodes, self.device)
-        arrays, det_arrays = self._record_arrays(rollout), self._record_arrays(det)
+        crec, cdet = self._compact(rollout), self._compact(det)
+        arrays = None if crec is not None else self._record_arrays(rollout)
+        det_arrays = None if cdet is not None else self._record_arrays(det)
+
+        def mb_graphs(rec, arrs, ix):
+            """Graphs of one minibatch, (mb * T, ...): slices of the full record, or (compact record) built by
+            K3 for just these environments."""
+            if rec is not None:
+                m = rec.graphs_of(ix, rec._goal, rec._obstacles)
+                arrs, ix = [m[k] for k in ("nodes", "edges", "receivers", "senders")], slice(None)
+            return U.chunk_graphs(arrs, ix, T, gi, torch.float32)
         n = self.n_agents
         rnn_det = det.rnn_states.reshape(b, T, n, RNN_DIM)
         st_pi, st_Vl, st_Vh = self._train_state("policy"), self._train_state("Vl"), self._train_state("Vh")
@@ -435,11 +484,11 @@ class DGPPO(Algorithm):
             self._np_rng.shuffle(idx)
             for mb in np.array_split(idx, max(1, b // mb_envs)):
                 ix = torch.as_tensor(mb, dtype=torch.long, device=self.device)
-                g = U.chunk_graphs(arrays, ix, T, gi, torch.float32)
+                g = mb_graphs(crec, arrays, ix)
                 loss = U.loss_Vl(st_Vl["tree"], g, pp["bT_Ql"][ix], gi, self.Vl_gnn_layers, self.rnn_step)
                 r = U.clip_and_step(st_Vl["opt"], st_Vl["leaves"], loss, self.max_grad_norm)
                 info.update({"Vl/loss": loss.detach(), "Vl/grad_norm": r["grad_norm"], "Vl/has_nan": r["has_nan"]})
-                gd = U.chunk_graphs(det_arrays, ix, T, gi, torch.float32)
+                gd = mb_graphs(cdet, det_arrays, ix)
                 loss = U.loss_Vh(st_Vh["tree"], gd, rnn_det[ix], pp["bTah_Qh_det"][ix], gi, self.Vh_gnn_layers)
                 r = U.clip_and_step(st_Vh["opt"], st_Vh["leaves"], loss, self.max_grad_norm)
                 info.update({"Vh/loss_Vh": loss.detach(), "Vh/grad_Vh_norm": r["grad_norm"],

@@ -95,8 +95,13 @@ __host__ __device__ inline GraphDims graph_dims(const DgppoEnvCfg& c) {
 
 // K2 with predict = 1 casts the rays from the position the agents will have AFTER the coming step
 // (computed from the current state, which is all it depends on); dgppo_lidar is predict = 0.
+// a_pitch / h_pitch: agent / hits are slots of (b, pitch, ...) records (1: plain batches).
 int launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent, const float* obstacles,
-                 const float* ray_dirs, float* hits, int32_t b, int predict);
+                 const float* ray_dirs, float* hits, int32_t b, int predict, int32_t a_pitch = 1, int32_t h_pitch = 1);
+// K1 with agent / next_agent / Lidar hits addressed as slots of (b, st_pitch, ...) records.
+int launch_env_step(void* stream, const DgppoEnvCfg* cfg, const float* agent, const float* goal,
+                    const float* obs_nodes, const float* action, float* next_agent, float* reward,
+                    float* cost, int32_t io_pitch, int32_t b, int32_t st_pitch);
 
 inline int check_env_cfg(const DgppoEnvCfg* c) {
   if (!c) return DGPPO_EINVAL;

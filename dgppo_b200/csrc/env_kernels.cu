@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32)
 env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ goal,
                 const float* __restrict__ obs_nodes, const float* __restrict__ action,
                 float* __restrict__ next_agent, float* __restrict__ reward,
-                float* __restrict__ cost, int io_pitch, int b) {
+                float* __restrict__ cost, int io_pitch, int b, int st_pitch) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * K1_WARPS + warp;
@@ -83,9 +83,10 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
   float* d2g = an2 + n;    // per-goal distance
   float* far = d2g + n;
 
-  const float* ag = agent + (size_t)env * n * sd;
+  // st_pitch: agent / next_agent / Lidar hits are slots of a (b, st_pitch, ...) record (1: plain batches)
+  const float* ag = agent + (size_t)env * st_pitch * n * sd;
   const float* ac = action + (size_t)env * io_pitch * n * 2;
-  float* nx = next_agent + (size_t)env * n * sd;
+  float* nx = next_agent + (size_t)env * st_pitch * n * sd;
 
   for (int i = lane; i < n; i += 32) {
     float s[5];
@@ -143,7 +144,7 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
     if (k.n_obs > 0) {
       float mo = INFINITY;
       if (lid) {
-        const float* h = obs_nodes + ((size_t)env * n + i) * k.top_k * 2;
+        const float* h = obs_nodes + ((size_t)env * st_pitch * n + i) * k.top_k * 2;
         for (int q = 0; q < k.top_k; ++q)
           mo = nanmin(mo, norm2(fsub(h[2 * q], xi), fsub(h[2 * q + 1], yi)));
         c1 = fsub(k.car, mo);
@@ -276,7 +277,8 @@ __device__ __forceinline__ void lidar_slot_near(float dx12, float dy12, float dx
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restrict__ obstacles,
-             const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd, int predict) {
+             const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd, int predict,
+             int a_pitch, int h_pitch) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long item = (long)blockIdx.x * K2_WARPS + warp;
@@ -293,10 +295,13 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   float* hx = reinterpret_cast<float*>(key + R);                // [R]
   float* hy = hx + R;
 
-  float x1 = agent[item * sd + 0], y1 = agent[item * sd + 1];
+  // slot-pointer addressing: env e of a (b, pitch, n, ...) record sits pitch * n rows after env e - 1
+  const long a_item = (long)env * a_pitch * n + (item - (long)env * n);
+  const long h_item = (long)env * h_pitch * n + (item - (long)env * n);
+  float x1 = agent[a_item * sd + 0], y1 = agent[a_item * sd + 1];
   if (predict) {                      // agent holds the state BEFORE the step: cast from where it will be after it
     float s[5];
-    for (int c = 0; c < sd; ++c) s[c] = agent[item * sd + c];
+    for (int c = 0; c < sd; ++c) s[c] = agent[a_item * sd + c];
     next_position(k, s, sd, x1, y1);
   }
   const float* ob = obstacles + (size_t)env * k.n_obs * DGPPO_OBS_STRIDE;
@@ -384,7 +389,7 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
   }
   __syncwarp();
   // ---- phase 3: stable top-k
-  float* out = hits + item * k.top_k * 2;
+  float* out = hits + h_item * k.top_k * 2;
   for (int r = lane; r < R; r += 32) {
     const unsigned long long kr = key[r];
     int rank = 0;
@@ -557,6 +562,12 @@ extern "C" int dgppo_graph_dims(const DgppoEnvCfg* cfg, DgppoGraphDims* out) {
 extern "C" int dgppo_env_step(void* stream, const DgppoEnvCfg* cfg, const float* agent,
                               const float* goal, const float* obs_nodes, const float* action,
                               float* next_agent, float* reward, float* cost, int32_t io_pitch, int32_t b) {
+  return dgppo::launch_env_step(stream, cfg, agent, goal, obs_nodes, action, next_agent, reward, cost, io_pitch, b, 1);
+}
+
+int dgppo::launch_env_step(void* stream, const DgppoEnvCfg* cfg, const float* agent, const float* goal,
+                           const float* obs_nodes, const float* action, float* next_agent, float* reward,
+                           float* cost, int32_t io_pitch, int32_t b, int32_t st_pitch) {
   if (int rc = check_env_cfg(cfg)) return rc;
   if (b == 0) return 0;
   if (b < 0 || io_pitch < 1 || !agent || !goal || !action || !next_agent || !reward || !cost) return DGPPO_EINVAL;
@@ -566,7 +577,7 @@ extern "C" int dgppo_env_step(void* stream, const DgppoEnvCfg* cfg, const float*
   if (smem > 48 * 1024) return DGPPO_ENOTSUP;
   const int grid = (b + K1_WARPS - 1) / K1_WARPS;
   env_step_kernel<<<grid, K1_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      k, agent, goal, obs_nodes, action, next_agent, reward, cost, io_pitch, b);
+      k, agent, goal, obs_nodes, action, next_agent, reward, cost, io_pitch, b, st_pitch);
   return (int)cudaGetLastError();
 }
 
@@ -576,7 +587,7 @@ extern "C" int dgppo_lidar(void* stream, const DgppoEnvCfg* cfg, const float* ag
 }
 
 int dgppo::launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent, const float* obstacles,
-                        const float* ray_dirs, float* hits, int32_t b, int predict) {
+                        const float* ray_dirs, float* hits, int32_t b, int predict, int32_t a_pitch, int32_t h_pitch) {
   if (int rc = check_env_cfg(cfg)) return rc;
   if (!is_lidar(cfg->kind) || cfg->n_obs == 0) return DGPPO_ENOTSUP;
   if (b == 0) return 0;
@@ -589,7 +600,7 @@ int dgppo::launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent
   if (items > 0x7fffffffL) return DGPPO_ENOTSUP;
   const int grid = (int)((items + K2_WARPS - 1) / K2_WARPS);
   lidar_kernel<<<grid, K2_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4, predict);
+      k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4, predict, a_pitch, h_pitch);
   return (int)cudaGetLastError();
 }
 

@@ -77,14 +77,43 @@ static int rollout_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg*
   if (int rc = check_env_cfg(env)) return rc;
   if (!net || !params || !B || T < 1 || b < 0) return DGPPO_EINVAL;
   if (b == 0) return 0;
-  if (!B->nodes || !B->edges || !B->states || !B->receivers || !B->senders || !B->node_type ||
-      !B->rnn || !B->actions || !B->rewards || !B->costs || !B->agent_ws || !B->goal)
-    return DGPPO_EINVAL;
+  if (!B->rnn || !B->actions || !B->rewards || !B->costs || !B->goal) return DGPPO_EINVAL;
   if (B->eps && !B->log_pis) return DGPPO_EINVAL;
   const GraphDims d = graph_dims(*env);
   const bool lid = is_lidar(env->kind);
-  if (d.n_on > 0 && (!B->obstacles || (lid && (!B->hits_ws || !B->ray_dirs)))) return DGPPO_EINVAL;
   const int n = d.n, P = T + 1;
+  if (B->agent_rec) {
+    // ---- compact record: K3's inputs per slot instead of the graph.  Per step: policy from the
+    // state of slot t (the GNN layers build the graph in their staging phase), K1 slot t -> t + 1, K2 slot t + 1.
+    if (d.n_on > 0 && (!B->obstacles || (lid && (!B->hits_rec || !B->ray_dirs)))) return DGPPO_EINVAL;
+    if (prof) return DGPPO_ENOTSUP;
+    const int nh = n_cost_of(env->kind), k2 = env->top_k * 2;
+    for (int t = 0; t < T; ++t) {
+      DgppoStateRecord st;
+      st.agent = B->agent_rec + (size_t)t * n * d.sd;
+      st.obs_nodes = (d.n_on == 0) ? nullptr : (lid ? B->hits_rec + (size_t)t * n * k2 : B->obstacles);
+      st.goal = B->goal;
+      int rc = dgppo_gnn_policy_from_state(stream, env, net, params, &st, P,
+                                           B->rnn + (size_t)t * n * 64, B->rnn + (size_t)(t + 1) * n * 64, P,
+                                           B->eps ? B->eps + (size_t)t * n * 2 : nullptr, T,
+                                           B->actions + (size_t)t * n * 2,
+                                           B->log_pis ? B->log_pis + (size_t)t * n : nullptr, T, b);
+      if (rc) return rc;
+      rc = launch_env_step(stream, env, st.agent, B->goal, st.obs_nodes, B->actions + (size_t)t * n * 2,
+                           B->agent_rec + (size_t)(t + 1) * n * d.sd, B->rewards + t,
+                           B->costs + (size_t)t * n * nh, T, b, P);
+      if (rc) return rc;
+      if (lid && d.n_on > 0) {
+        rc = launch_lidar(stream, env, B->agent_rec + (size_t)(t + 1) * n * d.sd, B->obstacles, B->ray_dirs,
+                          B->hits_rec + (size_t)(t + 1) * n * k2, b, 0, P, P);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  }
+  if (!B->nodes || !B->edges || !B->states || !B->receivers || !B->senders || !B->node_type || !B->agent_ws)
+    return DGPPO_EINVAL;
+  if (d.n_on > 0 && (!B->obstacles || (lid && (!B->hits_ws || !B->ray_dirs)))) return DGPPO_EINVAL;
   const size_t agent_sz = (size_t)b * n * d.sd;
   cudaStream_t main_st = (cudaStream_t)stream;
 

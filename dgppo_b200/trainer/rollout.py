@@ -37,30 +37,44 @@ def _submit_pool(n: int):
 class RolloutRecord:
     """Device buffers of one (b, T+1, ...) rollout record + kernel workspaces."""
 
-    def __init__(self, env: MultiAgentEnv, b: int, T: int, device: torch.device, stochastic: bool):
+    def __init__(self, env: MultiAgentEnv, b: int, T: int, device: torch.device, stochastic: bool,
+                 compact: bool = False):
+        """compact=True: the record keeps K3's INPUTS per slot (agent states, LiDAR hits) instead of the
+        GraphsTuple arrays - 2.9 KB instead of 10.7 KB per env-step at C3; graphs are built
+        on demand (`materialize`, `graphs_of`), the kernels read the state record directly (*_from_state)."""
         d = env.graph_dims()
         n = env.num_agents
         self.env, self.b, self.T, self.d, self.n = env, b, T, d, n
+        self.compact = compact
         f32 = dict(dtype=torch.float32, device=device)
         i32 = dict(dtype=torch.int32, device=device)
         P = T + 1
-        self.nodes = torch.empty((b, P, d.n_nodes, d.node_dim), **f32)
-        self.edges = torch.empty((b, P, d.n_edges, 4), **f32)
-        self.states = torch.empty((b, P, d.n_nodes, d.state_dim), **f32)
-        self.receivers = torch.empty((b, P, d.n_edges), **i32)
-        self.senders = torch.empty((b, P, d.n_edges), **i32)
-        self.node_type = torch.empty((b, P, d.n_nodes), **i32)
-        self.n_node = torch.empty((b, P), **i32)
-        self.n_edge = torch.empty((b, P), **i32)
+        self.agent_rec = self.hits_rec = None
+        self.nodes = self.edges = self.states = self.receivers = self.senders = self.node_type = None
+        self.n_node = self.n_edge = None
+        self._materialized = None
+        if compact:
+            self.agent_rec = torch.empty((b, P, n, d.state_dim), **f32)
+            if isinstance(env, LidarEnv) and d.n_obs_nodes > 0:
+                self.hits_rec = torch.empty((b, P, n, env.params["top_k_rays"], 2), **f32)
+        else:
+            self.nodes = torch.empty((b, P, d.n_nodes, d.node_dim), **f32)
+            self.edges = torch.empty((b, P, d.n_edges, 4), **f32)
+            self.states = torch.empty((b, P, d.n_nodes, d.state_dim), **f32)
+            self.receivers = torch.empty((b, P, d.n_edges), **i32)
+            self.senders = torch.empty((b, P, d.n_edges), **i32)
+            self.node_type = torch.empty((b, P, d.n_nodes), **i32)
+            self.n_node = torch.empty((b, P), **i32)
+            self.n_edge = torch.empty((b, P), **i32)
         self.rnn = torch.empty((b, P, n, RNN_DIM), **f32)
         self.actions = torch.empty((b, T, n, 2), **f32)
         self.log_pis = torch.empty((b, T, n), **f32) if stochastic else None
         self.rewards = torch.empty((b, T), **f32)
         self.costs = torch.empty((b, T, n, env.n_cost), **f32)
         self.dones = torch.zeros((b, T), dtype=torch.bool, device=device)
-        self.agent_ws = torch.empty((2, b, n, d.state_dim), **f32)
+        self.agent_ws = None if compact else torch.empty((2, b, n, d.state_dim), **f32)
         self.hits_ws = self.hits_ws2 = None
-        if isinstance(env, LidarEnv) and d.n_obs_nodes > 0:
+        if not compact and isinstance(env, LidarEnv) and d.n_obs_nodes > 0:
             self.hits_ws = torch.empty((b, n, env.params["top_k_rays"], 2), **f32)
             self.hits_ws2 = torch.empty_like(self.hits_ws)      # second buffer: LiDAR look-ahead (dgppo_rollout)
         self._init_graph_state()
@@ -95,24 +109,56 @@ class RolloutRecord:
 
     def nbytes(self) -> int:
         ts = [self.nodes, self.edges, self.states, self.receivers, self.senders, self.node_type,
-              self.n_node, self.n_edge, self.rnn, self.actions, self.rewards, self.costs, self.dones]
-        if self.log_pis is not None:
-            ts.append(self.log_pis)
-        return sum(t.numel() * t.element_size() for t in ts)
+              self.n_node, self.n_edge, self.agent_rec, self.hits_rec, self.rnn, self.actions, self.rewards,
+              self.costs, self.dones, self.log_pis]
+        return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+    def bytes_per_env_step(self) -> float:
+        return self.nbytes() / (self.b * self.T)
 
     _TENSORS = ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge", "rnn",
-                "actions", "log_pis", "rewards", "costs", "dones", "hits_ws", "hits_ws2")
+                "actions", "log_pis", "rewards", "costs", "dones", "hits_ws", "hits_ws2", "agent_rec", "hits_rec")
+
+    # ---- compact record: graphs on demand ------------------------------------------------------------
+    def graphs_of(self, env_idx: Optional[torch.Tensor], goal: torch.Tensor, obstacles: Optional[torch.Tensor]):
+        """Graph arrays (nodes, edges, states, receivers, senders, node_type, n_node, n_edge), each
+        (len(env_idx), T+1, ...), of the selected environments (all when None): ONE launch of K3
+        (dgppo_build_graph) over the stored states - bit for bit what the full record would hold."""
+        assert self.compact
+        env, d, n = self.env, self.d, self.n
+        ag = self.agent_rec if env_idx is None else self.agent_rec[env_idx]
+        m, P = ag.shape[0], self.T + 1
+        goal_s = goal if env_idx is None else goal[env_idx]
+        gl = goal_s.unsqueeze(1).expand(m, P, *goal_s.shape[1:]).reshape((m * P,) + tuple(goal_s.shape[1:])).contiguous()
+        if self.hits_rec is not None:
+            hr = self.hits_rec if env_idx is None else self.hits_rec[env_idx]
+            ob = hr.reshape(m * P, n, -1, 2).contiguous()
+        elif obstacles is not None and d.n_obs_nodes > 0:
+            o = obstacles if env_idx is None else obstacles[env_idx]
+            ob = o.unsqueeze(1).expand(m, P, *o.shape[1:]).reshape((m * P,) + tuple(o.shape[1:])).contiguous()
+        else:
+            ob = None
+        g = env._graph_kernel(ag.reshape(m * P, n, d.state_dim).contiguous(), gl, ob, None)
+        return {k: getattr(g, k).reshape((m, P) + tuple(getattr(g, k).shape[1:]))
+                for k in ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge")}
+
+    def materialize(self):
+        """All (b, T+1) graphs of a compact record (cached until the record is overwritten)."""
+        if self._materialized is None:
+            self._materialized = self.graphs_of(None, self._goal, self._obstacles)
+        return self._materialized
 
     def env_slice(self, lo: int, hi: int) -> "RolloutRecord":
         """A view of environments [lo, hi) of this record (shares memory)."""
         v = object.__new__(RolloutRecord)
         v.env, v.T, v.d, v.n, v.b = self.env, self.T, self.d, self.n, hi - lo
+        v.compact, v._materialized = self.compact, None
         for k in self._TENSORS:
             t = getattr(self, k)
             setattr(v, k, None if t is None else t[lo:hi])
         # the ping-pong state workspace must be contiguous per chunk: give the view its own
-        v.agent_ws = torch.empty((2, hi - lo) + tuple(self.agent_ws.shape[2:]), dtype=torch.float32,
-                                 device=self.agent_ws.device)
+        v.agent_ws = None if self.compact else torch.empty((2, hi - lo) + tuple(self.agent_ws.shape[2:]),
+                                                           dtype=torch.float32, device=self.rnn.device)
         v._init_graph_state()
         return v
 
@@ -121,6 +167,38 @@ class RolloutRecord:
         return GraphsTuple(self.n_node[:, s], self.n_edge[:, s], self.nodes[:, s], self.edges[:, s],
                            self.states[:, s], self.receivers[:, s], self.senders[:, s],
                            self.node_type[:, s], env_states)
+
+
+class LazyGraphsTuple:
+    """GraphsTuple-shaped view of slots [lo, hi) of a COMPACT record: the array fields are built by K3 from the
+    stored states on first access (`RolloutRecord.materialize`, one launch over all slots) and are then ordinary
+    tensors; `env_states` is available without building anything.  Iteration / indexing / `_replace` /
+    `type_states` behave like the GraphsTuple they stand for (utils/graph.py)."""
+
+    _FIELDS = GraphsTuple._FIELDS
+
+    def __init__(self, record: "RolloutRecord", lo: int, hi: int, env_states):
+        self.record, self.lo, self.hi, self.env_states, self.connectivity = record, lo, hi, env_states, None
+
+    def as_tuple(self) -> GraphsTuple:
+        m, s = self.record.materialize(), slice(self.lo, self.hi)
+        return GraphsTuple(m["n_node"][:, s], m["n_edge"][:, s], m["nodes"][:, s], m["edges"][:, s], m["states"][:, s],
+                           m["receivers"][:, s], m["senders"][:, s], m["node_type"][:, s], self.env_states)
+
+    def __getattr__(self, name):
+        if name in GraphsTuple._FIELDS or name in ("is_single", "n_graphs", "batch_shape", "type_nodes", "type_states",
+                                                   "map_arrays", "_replace", "without_edge"):
+            return getattr(self.as_tuple(), name)
+        raise AttributeError(name)
+
+    def __iter__(self):
+        return iter(self.as_tuple())
+
+    def __getitem__(self, i):
+        return self.as_tuple()[i]
+
+    def __len__(self):
+        return len(GraphsTuple._FIELDS)
 
 
 def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch.Tensor,
@@ -139,27 +217,32 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
     dev = graph0.nodes.device
     n = env.num_agents
     if record is None:
-        record = RolloutRecord(env, b, T, dev, stochastic=eps is not None)
+        record = RolloutRecord(env, b, T, dev, stochastic=eps is not None,
+                               compact=os.environ.get("DGPPO_COMPACT", "0") == "1")
     rec, d = record, record.d
     assert rec.b == b and rec.T == T
     es = graph0.env_states
 
     # slot 0 <- the reset graph; workspaces <- the reset state
-    for name in ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge"):
-        getattr(rec, name)[:, 0].copy_(getattr(graph0, name))
+    compact = rec.compact
+    rec._materialized = None
+    if not compact:
+        for name in ("nodes", "edges", "states", "receivers", "senders", "node_type", "n_node", "n_edge"):
+            getattr(rec, name)[:, 0].copy_(getattr(graph0, name))
     if init_rnn_state is None:
         rec.rnn[:, 0].zero_()
     else:   # (rnn_layers=1, n, n_carries=1, 64) as algo.init_rnn_state (informarl.py:114-124)
         rec.rnn[:, 0].copy_(init_rnn_state.reshape(n, RNN_DIM).to(dev))
-    rec.agent_ws[0].copy_(es.agent)
+    (rec.agent_rec[:, 0] if compact else rec.agent_ws[0]).copy_(es.agent)
     goal = es.goal.contiguous()
     obstacles, rays = None, None
     if isinstance(es, LidarEnvState):
-        if rec.hits_ws is not None:
+        if (rec.hits_rec if compact else rec.hits_ws) is not None:
             obstacles = es.obstacle.record.contiguous()
             rays = env.ray_dirs(dev)
             k = env.params["top_k_rays"]
-            rec.hits_ws.copy_(graph0.states[:, n + env.num_goals:n + env.num_goals + n * k, :2].reshape(b, n, k, 2))
+            hits0 = graph0.states[:, n + env.num_goals:n + env.num_goals + n * k, :2].reshape(b, n, k, 2)
+            (rec.hits_rec[:, 0] if compact else rec.hits_ws).copy_(hits0)
     elif isinstance(es, MPEEnvState) and es.obs is not None:
         obstacles = es.obs.contiguous()
     if eps is not None:
@@ -184,7 +267,9 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
         ptr(rec.nodes), ptr(rec.edges), ptr(rec.states), ptr(rec.receivers), ptr(rec.senders),
         ptr(rec.node_type), ptr(rec.n_node), ptr(rec.n_edge), ptr(rec.rnn), ptr(eps),
         ptr(rec.actions), ptr(rec.log_pis) if eps is not None else None, ptr(rec.rewards), ptr(rec.costs),
-        ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays), ptr(rec.hits_ws2))
+        ptr(rec.agent_ws), ptr(rec.hits_ws), ptr(goal), ptr(obstacles), ptr(rays), ptr(rec.hits_ws2),
+        ptr(rec.agent_rec), ptr(rec.hits_rec))
+    rec._goal, rec._obstacles = goal, obstacles        # what graphs_of / the *_from_state kernels need later
     cfg = env.env_cfg()
     if use_graph:
         key = (bytes(cfg), bytes(net_cfg), T, b, os.environ.get("DGPPO_HEAD"), os.environ.get("DGPPO_LIDAR_AHEAD"))
@@ -202,19 +287,34 @@ def run_rollout(env: MultiAgentEnv, net_cfg: _lib.DgppoNetCfg, params_dev: torch
         _lib.check(_lib.lib().dgppo_rollout(stream_ptr(), C.byref(cfg), C.byref(net_cfg), ptr(params_dev),
                                              C.byref(buf), T, b, prof), "dgppo_rollout")
 
-    sd = d.state_dim
+    return _as_rollout(env, rec, es, eps is not None, T, test_mode)
+
+
+def _as_rollout(env, rec, es, stochastic: bool, T: int, test_mode: bool) -> Rollout:
+    n = env.num_agents
+
     def env_view(lo, hi):
-        st = rec.states[:, lo:hi]
+        if rec.compact:     # per-slot agent states; goals are static (the reference repeats them per step)
+            ag = rec.agent_rec[:, lo:hi]
+            gl = es.goal.unsqueeze(1).expand(ag.shape[0], hi - lo, *es.goal.shape[1:])
+        else:
+            st = rec.states[:, lo:hi]
+            ag, gl = st[:, :, :n], st[:, :, n:n + env.num_goals]
         if isinstance(es, LidarEnvState):
-            return LidarEnvState(st[:, :, :n], st[:, :, n:n + env.num_goals], es.obstacle)
-        return MPEEnvState(st[:, :, :n], st[:, :, n:n + env.num_goals], es.obs)
+            return LidarEnvState(ag, gl, es.obstacle)
+        return MPEEnvState(ag, gl, es.obs)
     rnn = rec.rnn[:, 1:] if test_mode else rec.rnn[:, :T]
+    if rec.compact:
+        return Rollout(graph=LazyGraphsTuple(rec, 0, T, env_view(0, T)), actions=rec.actions,
+                       rnn_states=rnn.unsqueeze(2).unsqueeze(4), rewards=rec.rewards, costs=rec.costs, dones=rec.dones,
+                       log_pis=rec.log_pis if stochastic else None,
+                       next_graph=LazyGraphsTuple(rec, 1, T + 1, env_view(1, T + 1)))
     return Rollout(
         graph=rec.graph_view(0, T, env_view(0, T)),
         actions=rec.actions,
         rnn_states=rnn.unsqueeze(2).unsqueeze(4),           # (b, T, rnn_layers=1, n, n_carries=1, 64)
         rewards=rec.rewards, costs=rec.costs, dones=rec.dones,
-        log_pis=rec.log_pis if eps is not None else None,
+        log_pis=rec.log_pis if stochastic else None,
         next_graph=rec.graph_view(1, T + 1, env_view(1, T + 1)))
 
 
@@ -238,7 +338,8 @@ def run_rollout_chunked(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state
     if n_chunks <= 1 or b < 2 * n_chunks:
         return run_rollout(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state, record, test_mode, prof)
     if record is None:
-        record = RolloutRecord(env, b, T, dev, stochastic=eps is not None)
+        record = RolloutRecord(env, b, T, dev, stochastic=eps is not None,
+                               compact=os.environ.get("DGPPO_COMPACT", "0") == "1")
     if not hasattr(record, "_chunks") or len(record._chunks) != n_chunks:
         bounds = [(i * b) // n_chunks for i in range(n_chunks + 1)]
         record._chunks = [(lo, hi, record.env_slice(lo, hi), torch.cuda.Stream(device=dev))
@@ -269,15 +370,9 @@ def run_rollout_chunked(env, net_cfg, params_dev, graph0, eps, T, init_rnn_state
         dones = [submit(i) for i in range(n_chunks)]
     for done in dones:
         cur.wait_event(done)
-    rec, n, es = record, env.num_agents, graph0.env_states
-
-    def env_view(lo, hi):
-        stt = rec.states[:, lo:hi]
-        if isinstance(es, LidarEnvState):
-            return LidarEnvState(stt[:, :, :n], stt[:, :, n:n + env.num_goals], es.obstacle)
-        return MPEEnvState(stt[:, :, :n], stt[:, :, n:n + env.num_goals], es.obs)
-    rnn = rec.rnn[:, 1:] if test_mode else rec.rnn[:, :T]
-    return Rollout(graph=rec.graph_view(0, T, env_view(0, T)), actions=rec.actions,
-                   rnn_states=rnn.unsqueeze(2).unsqueeze(4), rewards=rec.rewards, costs=rec.costs, dones=rec.dones,
-                   log_pis=rec.log_pis if eps is not None else None,
-                   next_graph=rec.graph_view(1, T + 1, env_view(1, T + 1)))
+    record._goal = graph0.env_states.goal.contiguous()
+    es0 = graph0.env_states
+    record._obstacles = (es0.obstacle.record.contiguous() if isinstance(es0, LidarEnvState) and es0.obstacle is not None
+                         else (es0.obs.contiguous() if isinstance(es0, MPEEnvState) and es0.obs is not None else None))
+    record._materialized = None
+    return _as_rollout(env, record, graph0.env_states, eps is not None, T, test_mode)

@@ -371,6 +371,13 @@ typedef struct DgppoRolloutBuffers {
   float* agent_ws; float* hits_ws;
   const float* goal; const float* obstacles; const float* ray_dirs;
   float* hits_ws2;
+  /* COMPACT record: when agent_rec is non-NULL the graph fields above (nodes ... n_edge) and the
+   * workspaces are not used (may be NULL); the rollout stores K3's inputs per slot instead -
+   *   agent_rec (b, T+1, n, state_dim), slot 0 = the reset state (caller-initialised);
+   *   hits_rec  (b, T+1, n, top_k, 2)   (Lidar with obstacles; slot 0 = the hits of the reset state)
+   * - and the policy runs through dgppo_gnn_policy_from_state.  K3 is not launched at all: a GraphsTuple for any
+   * slot is dgppo_build_graph of that slot's state (bit-identical to what the full record would hold).        */
+  float* agent_rec; float* hits_rec;
 } DgppoRolloutBuffers;
 
 int dgppo_rollout(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg* net,
