@@ -101,7 +101,7 @@ class DGPPO(Algorithm):
         # independent env groups run on separate streams so env kernels overlap policy kernels
         # compact rollout records: K3's inputs per slot instead of the graph arrays; the value
         # kernels and the update read them directly, GraphsTuple views are built on demand
-        self.compact_record = bool(kwargs.get("compact_record", os.environ.get("DGPPO_COMPACT", "0") == "1"))
+        self.compact_record = bool(kwargs.get("compact_record", os.environ.get("DGPPO_COMPACT", "1") == "1"))
         # (DGPPO_ROLLOUT_CHUNKS overrides; default by batch size, _n_chunks)
         self.rollout_chunks = int(os.environ.get("DGPPO_ROLLOUT_CHUNKS", "0"))
 

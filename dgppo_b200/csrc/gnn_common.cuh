@@ -45,30 +45,33 @@ struct GnnArgs {
 // from the state arrays (lidar_env/base.py:234-264, mpe/base.py:214-233); row in [0, N - 1)
 __device__ __forceinline__ void node_row_from_state(const GnnArgs& g, int env, int slot, int row, float* dst) {
   const int n = g.n, gn = g.g_nodes, sd = g.sd;
-  float v[X0S];
-#pragma unroll
-  for (int c = 0; c < X0S; ++c) v[c] = 0.f;
-  if (row < n) {
-    const float* s = g.c_agent + (((size_t)env * g.c_pitch + slot) * n + row) * sd;
-    for (int c = 0; c < sd; ++c) v[c] = __ldg(s + c);
-    v[sd + 2] = 1.f;
-  } else if (row < n + gn) {
-    const float* s = g.c_goal + ((size_t)env * gn + (row - n)) * sd;
-    for (int c = 0; c < sd; ++c) v[c] = __ldg(s + c);
-    v[sd + 1] = 1.f;
-  } else {
-    const int o = row - n - gn;
-    if (g.c_lidar) {
-      const float* s = g.c_obs + (((size_t)env * g.c_pitch + slot) * (size_t)(g.N - 1 - n - gn) + o) * 2;
-      v[0] = __ldg(s); v[1] = __ldg(s + 1);
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;      // columns 0-3, 4-7 (no indexed local array: registers)
+  int type;                                                  // 0 agent, 1 goal, 2 obstacle
+  if (row < n + gn) {
+    type = row < n ? 0 : 1;
+    const float* s = type == 0 ? g.c_agent + (((size_t)env * g.c_pitch + slot) * n + row) * sd
+                               : g.c_goal + ((size_t)env * gn + (row - n)) * sd;
+    if (sd == 4) {
+      lo = __ldg(reinterpret_cast<const float4*>(s));
     } else {
-      const float* s = g.c_obs + ((size_t)env * (g.N - 1 - n - gn) + o) * 4;
-      for (int c = 0; c < 4; ++c) v[c] = __ldg(s + c);
+      lo = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
+      hi.x = __ldg(s + 4);
     }
-    v[sd] = 1.f;
+  } else {
+    type = 2;
+    const int o = row - n - gn, n_on = g.N - 1 - n - gn;
+    if (g.c_lidar) {
+      const float2 h = __ldg(reinterpret_cast<const float2*>(g.c_obs + (((size_t)env * g.c_pitch + slot) * (size_t)n_on + o) * 2));
+      lo.x = h.x; lo.y = h.y;
+    } else {
+      lo = __ldg(reinterpret_cast<const float4*>(g.c_obs + ((size_t)env * n_on + o) * 4));
+    }
   }
-#pragma unroll
-  for (int c = 0; c < X0S; ++c) dst[c] = v[c];
+  // one-hot at column sd + (2 - type): [obstacle, goal, agent] = columns sd, sd + 1, sd + 2
+  const int c1 = sd + 2 - type;
+  if (c1 == 4) hi.x = 1.f; else if (c1 == 5) hi.y = 1.f; else if (c1 == 6) hi.z = 1.f; else hi.w = 1.f;
+  reinterpret_cast<float4*>(dst)[0] = lo;
+  reinterpret_cast<float4*>(dst)[1] = hi;
 }
 
 // state2feat of a staged node row (identity, or [x, y, v cos, v sin] for the bicycle: lidar_bicycle_target.py:113-118)

@@ -86,9 +86,28 @@ static int rollout_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg*
     // ---- compact record: K3's inputs per slot instead of the graph.  Per step: policy from the
     // state of slot t (the GNN layers build the graph in their staging phase), K1 slot t -> t + 1, K2 slot t + 1.
     if (d.n_on > 0 && (!B->obstacles || (lid && (!B->hits_rec || !B->ray_dirs)))) return DGPPO_EINVAL;
-    if (prof) return DGPPO_ENOTSUP;
     const int nh = n_cost_of(env->kind), k2 = env->top_k * 2;
+    // LiDAR look-ahead as a parallel graph branch (captured rollouts of small batches, as below): the hits of slot
+    // t + 1 depend on the state of slot t only, so they are cast from it (predict = 1) while the policy of step t runs.
+    static const char* ahead_env_c = getenv("DGPPO_LIDAR_AHEAD");
+    const bool on_c = ahead_env_c && ahead_env_c[0] == '1', off_c = ahead_env_c && ahead_env_c[0] == '0';
+    const bool ahead_c = lid && d.n_on > 0 && !prof && (keep ? (on_c || (!off_c && b < 1024)) : false);
+    AheadRes unused_c;
+    AheadRes& res_c = keep ? *keep : unused_c;      // only used when ahead_c (keep != nullptr then)
+    if (ahead_c) {
+      if (cudaStreamCreateWithFlags(&res_c.side, cudaStreamNonBlocking) != cudaSuccess) return DGPPO_EINVAL;
+      res_c.ev.assign((size_t)2 * (T + 1), nullptr);   // [2 t] state of slot t ready (main), [2 t + 1] hits of slot t ready (side)
+      for (auto& e : res_c.ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return DGPPO_EINVAL;
+      cudaEventRecord(res_c.ev[0], (cudaStream_t)stream);
+      cudaStreamWaitEvent(res_c.side, res_c.ev[0], 0);
+      if (int rc = launch_lidar(res_c.side, env, B->agent_rec, B->obstacles, B->ray_dirs, B->hits_rec + (size_t)n * k2,
+                                b, 1, P, P)) return rc;
+      cudaEventRecord(res_c.ev[3], res_c.side);
+    }
     for (int t = 0; t < T; ++t) {
+      mark(t, 0);
+      if (ahead_c && t >= 1) cudaStreamWaitEvent((cudaStream_t)stream, res_c.ev[2 * t + 1], 0);   // hits of slot t
       DgppoStateRecord st;
       st.agent = B->agent_rec + (size_t)t * n * d.sd;
       st.obs_nodes = (d.n_on == 0) ? nullptr : (lid ? B->hits_rec + (size_t)t * n * k2 : B->obstacles);
@@ -99,16 +118,31 @@ static int rollout_impl(void* stream, const DgppoEnvCfg* env, const DgppoNetCfg*
                                            B->actions + (size_t)t * n * 2,
                                            B->log_pis ? B->log_pis + (size_t)t * n : nullptr, T, b);
       if (rc) return rc;
+      mark(t, 1);
       rc = launch_env_step(stream, env, st.agent, B->goal, st.obs_nodes, B->actions + (size_t)t * n * 2,
                            B->agent_rec + (size_t)(t + 1) * n * d.sd, B->rewards + t,
                            B->costs + (size_t)t * n * nh, T, b, P);
       if (rc) return rc;
-      if (lid && d.n_on > 0) {
+      mark(t, 2);
+      if (ahead_c) {
+        if (t + 2 <= T) {        // state of slot t + 1 exists: cast the hits of slot t + 2 from it on the side branch
+          cudaEventRecord(res_c.ev[2 * (t + 1)], (cudaStream_t)stream);
+          cudaStreamWaitEvent(res_c.side, res_c.ev[2 * (t + 1)], 0);
+          rc = launch_lidar(res_c.side, env, B->agent_rec + (size_t)(t + 1) * n * d.sd, B->obstacles, B->ray_dirs,
+                            B->hits_rec + (size_t)(t + 2) * n * k2, b, 1, P, P);
+          if (rc) return rc;
+          cudaEventRecord(res_c.ev[2 * (t + 2) + 1], res_c.side);
+        }
+      } else if (lid && d.n_on > 0) {
         rc = launch_lidar(stream, env, B->agent_rec + (size_t)(t + 1) * n * d.sd, B->obstacles, B->ray_dirs,
                           B->hits_rec + (size_t)(t + 1) * n * k2, b, 0, P, P);
         if (rc) return rc;
       }
+      mark(t, 3);
+      mark(t, 4);                                // no graph kernel in the loop
     }
+    if (ahead_c) cudaStreamWaitEvent((cudaStream_t)stream, res_c.ev[2 * T + 1], 0);   // join: hits of the last slot
+    if (prof) prof->recorded = true;
     return 0;
   }
   if (!B->nodes || !B->edges || !B->states || !B->receivers || !B->senders || !B->node_type || !B->agent_ws)
