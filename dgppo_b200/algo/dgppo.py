@@ -131,9 +131,7 @@ class DGPPO(Algorithm):
         self._packed.pop(name, None)
         st = self._train.get(name)
         if st is not None:
-            with torch.no_grad():
-                for (path, leaf), t in zip(U.tree_leaves(tree), st["leaves"]):
-                    t.copy_(torch.as_tensor(np.asarray(leaf), dtype=t.dtype, device=t.device))
+            st.load(tree)
 
     def invalidate(self, name: Optional[str] = None) -> None:
         """Drop the packed device copy of `name` (all nets when None).  Needed only after editing the NumPy
@@ -414,19 +412,17 @@ class DGPPO(Algorithm):
         return A, deriv, acbf, safe.bool()
 
     # -------------------------------------------------------------------- update
-    def _train_state(self, name: str) -> dict:
+    def _train_state(self, name: str) -> "U.NetTrainState":
         st = self._train.get(name)
         if st is None:
-            tree = U.to_torch_tree(self._trees[name], self.device)
-            leaves = [t for _, t in U.tree_leaves(tree)]
-            st = {"tree": tree, "leaves": leaves, "opt": U.AdamIfFinite(leaves, self._lrs[name])}
+            st = U.NetTrainState(self._trees[name], self.device, self._lrs[name])
             self._train[name] = st
         return st
 
     def _sync_params_from_training(self) -> None:
-        """Training leaves -> the NumPy pytrees `params` exposes (and the kernels' packed copies)."""
+        """Training parameters -> the NumPy pytrees `params` exposes (and the kernels' packed copies)."""
         for name, st in self._train.items():
-            self._trees[name] = U.to_numpy_tree(st["tree"])
+            self._trees[name] = st.numpy_tree()
             self._packed.pop(name, None)
 
     def prepass(self, rollout: Rollout, step: int) -> dict:
@@ -478,6 +474,27 @@ class DGPPO(Algorithm):
         n = self.n_agents
         rnn_det = det.rnn_states.reshape(b, T, n, RNN_DIM)
         st_pi, st_Vl, st_Vh = self._train_state("policy"), self._train_state("Vl"), self._train_state("Vh")
+
+        def minibatch_step(nodes, edge_feat, sidx, mask, d_nodes, d_edge_feat, d_sidx, d_mask, Ql, rnn_d, Qh_d, act, lp_old,
+                           adv, eps):
+            """update_fn body (dgppo.py:278-287): Vl, Vh, policy - each: loss, gradient, all-reduce, clip, Adam."""
+            g = {"nodes": nodes, "edge_feat": edge_feat, "sidx": sidx, "mask": mask}
+            gd = {"nodes": d_nodes, "edge_feat": d_edge_feat, "sidx": d_sidx, "mask": d_mask}
+            out = {}
+            loss = U.loss_Vl(st_Vl.tree(), g, Ql, gi, self.Vl_gnn_layers, self.rnn_step)
+            r = st_Vl.step(loss, self.max_grad_norm)
+            out.update({"Vl/loss": loss.detach(), "Vl/grad_norm": r["grad_norm"], "Vl/has_nan": r["has_nan"]})
+            loss = U.loss_Vh(st_Vh.tree(), gd, rnn_d, Qh_d, gi, self.Vh_gnn_layers)
+            r = st_Vh.step(loss, self.max_grad_norm)
+            out.update({"Vh/loss_Vh": loss.detach(), "Vh/grad_Vh_norm": r["grad_norm"], "Vh/grad_Vh_has_nan": r["has_nan"]})
+            loss, pinfo = U.loss_policy(st_pi.tree(), g, act, lp_old, adv, eps, gi, self.actor_gnn_layers, self.rnn_step,
+                                        self.clip_eps, self.coef_ent)
+            r = st_pi.step(loss, self.max_grad_norm)
+            out.update({"policy/loss": loss.detach(), "policy/grad_norm": r["grad_norm"], "policy/has_nan": r["has_nan"],
+                        **{k: v.detach() for k, v in pinfo.items()}})
+            return out
+
+        use_graph = os.environ.get("DGPPO_UPDATE_GRAPH", "1") != "0"
         info = {}
         for _ in range(self.epoch_ppo):
             idx = np.arange(b)
@@ -485,21 +502,22 @@ class DGPPO(Algorithm):
             for mb in np.array_split(idx, max(1, b // mb_envs)):
                 ix = torch.as_tensor(mb, dtype=torch.long, device=self.device)
                 g = mb_graphs(crec, arrays, ix)
-                loss = U.loss_Vl(st_Vl["tree"], g, pp["bT_Ql"][ix], gi, self.Vl_gnn_layers, self.rnn_step)
-                r = U.clip_and_step(st_Vl["opt"], st_Vl["leaves"], loss, self.max_grad_norm)
-                info.update({"Vl/loss": loss.detach(), "Vl/grad_norm": r["grad_norm"], "Vl/has_nan": r["has_nan"]})
                 gd = mb_graphs(cdet, det_arrays, ix)
-                loss = U.loss_Vh(st_Vh["tree"], gd, rnn_det[ix], pp["bTah_Qh_det"][ix], gi, self.Vh_gnn_layers)
-                r = U.clip_and_step(st_Vh["opt"], st_Vh["leaves"], loss, self.max_grad_norm)
-                info.update({"Vh/loss_Vh": loss.detach(), "Vh/grad_Vh_norm": r["grad_norm"],
-                             "Vh/grad_Vh_has_nan": r["has_nan"]})
                 eps = torch.randn(rollout.actions[ix].shape, generator=self._gen, device=self.device)
-                loss, pinfo = U.loss_policy(st_pi["tree"], g, rollout.actions[ix], rollout.log_pis[ix],
-                                            pp["bTa_A"][ix], eps, gi, self.actor_gnn_layers, self.rnn_step,
-                                            self.clip_eps, self.coef_ent)
-                r = U.clip_and_step(st_pi["opt"], st_pi["leaves"], loss, self.max_grad_norm)
-                info.update({"policy/loss": loss.detach(), "policy/grad_norm": r["grad_norm"],
-                             "policy/has_nan": r["has_nan"], **pinfo})
+                inputs = (g["nodes"], g["edge_feat"], g["sidx"], g["mask"], gd["nodes"], gd["edge_feat"], gd["sidx"],
+                          gd["mask"], pp["bT_Ql"][ix], rnn_det[ix], pp["bTah_Qh_det"][ix], rollout.actions[ix],
+                          rollout.log_pis[ix], pp["bTa_A"][ix], eps)
+                if use_graph:
+                    # the whole minibatch step replayed as one CUDA graph (captured once per minibatch shape)
+                    key = ("update_graph", tuple((tuple(x.shape), x.dtype) for x in inputs))
+                    gs = self._workspaces.get(key)
+                    if gs is None:
+                        states = st_Vl.state_tensors() + st_Vh.state_tensors() + st_pi.state_tensors()
+                        gs = U.GraphedStep(minibatch_step, inputs, states)
+                        self._workspaces[key] = gs
+                    info = dict(gs(*inputs))
+                else:
+                    info = minibatch_step(*inputs)
         self._sync_params_from_training()
         info["policy/log_pi_min"] = rollout.log_pis.min()
         info["Vl/max_target"], info["Vl/min_target"] = pp["bT_Ql"].max(), pp["bT_Ql"].min()

@@ -259,6 +259,115 @@ def loss_policy(params, g, actions, log_pis_old, adv, eps, gi, n_layers, rnn_ste
 
 
 # --------------------------------------------------------------- optimiser
+class NetTrainState:
+    """Parameters of one net as ONE flat fp32 tensor (the leaves are views of it, rebuilt per step), with the
+    state of optax.apply_if_finite(optax.adam(lr), ...) (b1 0.9, b2 0.999, eps 1e-8) beside it.  Flat because the
+    gradient all-reduce wants one buffer and because the whole step then is a handful of kernels with no host
+    synchronisation - which is what lets it be captured in a CUDA graph (GraphedStep)."""
+
+    def __init__(self, tree_np, device, lr: float, dtype=torch.float32, b1=0.9, b2=0.999, eps=1e-8):
+        self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
+        self.meta, off, chunks = [], 0, []
+        for path, leaf in tree_leaves(tree_np):
+            a = np.asarray(leaf)
+            self.meta.append((path, tuple(a.shape), off, a.size))
+            chunks.append(torch.as_tensor(a.reshape(-1), dtype=dtype))
+            off += a.size
+        self.flat = torch.cat(chunks).to(device).requires_grad_(True)
+        self.m = torch.zeros_like(self.flat, requires_grad=False)
+        self.v = torch.zeros_like(self.flat, requires_grad=False)
+        self.count = torch.zeros((), dtype=torch.float64, device=device)         # applied steps
+        self.notfinite_count = torch.zeros((), dtype=torch.float64, device=device)
+
+    def state_tensors(self):
+        return [self.flat, self.m, self.v, self.count, self.notfinite_count]
+
+    def tree(self):
+        """Nested dict of (differentiable) views of the flat parameter tensor."""
+        out = {}
+        for path, shape, off, size in self.meta:
+            node = out
+            for k in path[:-1]:
+                node = node.setdefault(k, {})
+            node[path[-1]] = self.flat[off:off + size].view(shape)
+        return out
+
+    def numpy_tree(self):
+        flat = self.flat.detach().to(torch.float32).cpu().numpy()
+        out = {}
+        for path, shape, off, size in self.meta:
+            node = out
+            for k in path[:-1]:
+                node = node.setdefault(k, {})
+            node[path[-1]] = flat[off:off + size].reshape(shape).copy()
+        return out
+
+    @torch.no_grad()
+    def load(self, tree_np):
+        for (path, leaf), (p2, shape, off, size) in zip(tree_leaves(tree_np), self.meta):
+            assert path == p2
+            self.flat[off:off + size].copy_(torch.as_tensor(np.asarray(leaf).reshape(-1), dtype=self.flat.dtype))
+
+    def step(self, loss: torch.Tensor, max_norm: float) -> dict:
+        """grad -> mean all-reduce over the ranks (the flat buffer itself) -> has_any_nan_or_inf ->
+        compute_norm_and_clip (trainer/utils.py:113-118: g / max(max_norm, |g|) * max_norm) -> Adam, skipped as a
+        whole when the gradient is not finite.  No host synchronisation: the skip is a 0 / 1 factor."""
+        (g,) = torch.autograd.grad(loss, [self.flat])
+        (g,) = D.allreduce_mean_flat([g])
+        with torch.no_grad():
+            sq = (g * g).sum()
+            g_norm = torch.sqrt(sq)
+            ok = torch.isfinite(sq)
+            f = ok.to(self.flat.dtype)
+            g = torch.where(ok, g * (max_norm / torch.clamp(g_norm, min=max_norm)), torch.zeros_like(g))
+            self.count += ok.to(torch.float64)
+            self.notfinite_count += (~ok).to(torch.float64)
+            cnt = torch.clamp(self.count, min=1.0)
+            c1 = (1.0 - self.b1 ** cnt).to(self.flat.dtype)
+            c2 = (1.0 - self.b2 ** cnt).to(self.flat.dtype)
+            self.m += f * (1.0 - self.b1) * (g - self.m)
+            self.v += f * (1.0 - self.b2) * (g * g - self.v)
+            self.flat -= f * (self.lr / c1) * self.m / (torch.sqrt(self.v / c2) + self.eps)
+        return {"grad_norm": g_norm, "has_nan": 1.0 - f}
+
+
+class GraphedStep:
+    """A training step `fn(*tensors) -> dict of 0-dim tensors` captured in a CUDA graph: inputs are copied into
+    static buffers, the step (forward, backward, all-reduce, clip, Adam) is replayed with one launch.  The eager
+    step issues several thousand small kernels (16 recurrent steps x three nets, forward and backward); replay
+    removes their launch cost.  Warm-up iterations run for real (as capture requires), so the optimiser state
+    is restored afterwards from a snapshot."""
+
+    def __init__(self, fn, inputs, state_tensors):
+        self.fn = fn
+        self.static_in = [x.clone() for x in inputs]
+        saved = [t.detach().clone() for t in state_tensors]
+
+        def restore():
+            with torch.no_grad():
+                for t, s_ in zip(state_tensors, saved):
+                    t.copy_(s_)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn(*self.static_in)
+        cur.wait_stream(side)
+        restore()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(*self.static_in)
+        restore()
+
+    def __call__(self, *inputs):
+        for s_, x in zip(self.static_in, inputs):
+            s_.copy_(x)
+        self.graph.replay()
+        return self.out
+
+
+# legacy list-of-leaves optimiser (kept for the unit tests of the Adam / clip arithmetic)
 class AdamIfFinite:
     """optax.apply_if_finite(optax.adam(lr), max_consecutive_errors) on a list of leaves
     (b1 0.9, b2 0.999, eps 1e-8): a step with any non-finite gradient is skipped."""

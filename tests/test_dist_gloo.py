@@ -67,20 +67,18 @@ def _update_worker(rank, world, port, out):
         def run(rows, distributed):
             sel = {k: v.reshape((mb, T) + v.shape[1:])[rows].reshape((len(rows) * T,) + v.shape[1:]) for k, v in gr.items()}
             tg, gi = torch_graph(sel, dims, torch.float64)
-            tree = U.to_torch_tree(vh, "cpu", torch.float64)
-            leaves = [t for _, t in U.tree_leaves(tree)]
-            opt = U.AdamIfFinite(leaves, 1e-3)
-            loss = U.loss_Vh(tree, tg, torch.tensor(hs[rows]), torch.tensor(tgt[rows]), gi, 1)
+            st = U.NetTrainState(vh, "cpu", 1e-3, dtype=torch.float64)        # the product path's optimiser state
+            loss = U.loss_Vh(st.tree(), tg, torch.tensor(hs[rows]), torch.tensor(tgt[rows]), gi, 1)
             if distributed:
-                U.clip_and_step(opt, leaves, loss, 2.0)
+                st.step(loss, 2.0)
             else:       # single process: same code path with the collective switched off
                 saved = U.D.allreduce_mean_flat
                 U.D.allreduce_mean_flat = lambda g: list(g)
                 try:
-                    U.clip_and_step(opt, leaves, loss, 2.0)
+                    st.step(loss, 2.0)
                 finally:
                     U.D.allreduce_mean_flat = saved
-            return torch.cat([t.detach().reshape(-1) for t in leaves])
+            return st.flat.detach().clone()
         mine = run(list(range(rank * mb // world, (rank + 1) * mb // world)), True)
         full = run(list(range(mb)), False)
         assert torch.allclose(mine, full, rtol=1e-9, atol=1e-12), float((mine - full).abs().max())

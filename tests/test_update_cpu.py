@@ -219,3 +219,38 @@ def test_adam_if_finite_and_clip():
     o2 = U.AdamIfFinite(q, lr=0.01)
     U.clip_and_step(o2, q, (q[0] ** 2).sum(), max_norm=2.0)
     np.testing.assert_allclose(o2.m[0].numpy(), 0.1 * 0.2, rtol=1e-12)
+
+
+def test_flat_train_state_matches_leafwise_adam():
+    """NetTrainState.step (flat buffer, sync-free skip) == clip_and_step on the list of leaves, step by step, and a
+    non-finite gradient leaves parameters and moments untouched."""
+    rng = np.random.default_rng(0)
+    tree = {"params": {"a": {"kernel": rng.standard_normal((3, 4)), "bias": rng.standard_normal(4)},
+                       "b": {"kernel": rng.standard_normal((4, 2))}}}
+    st = U.NetTrainState(tree, "cpu", lr=0.05, dtype=torch.float64)
+    ref_tree = U.to_torch_tree(tree, "cpu", torch.float64)
+    ref_leaves = [t for _, t in U.tree_leaves(ref_tree)]
+    opt = U.AdamIfFinite(ref_leaves, 0.05)
+    x = torch.tensor(rng.standard_normal((5, 3)))
+
+    def loss_of(t):
+        return ((x @ t["params"]["a"]["kernel"] + t["params"]["a"]["bias"]) @ t["params"]["b"]["kernel"]).pow(2).sum() * 7.0
+    for it in range(4):
+        r1 = st.step(loss_of(st.tree()), 2.0)
+        r2 = U.clip_and_step(opt, ref_leaves, loss_of(ref_tree), 2.0)
+        np.testing.assert_allclose(float(r1["grad_norm"]), float(r2["grad_norm"]), rtol=1e-12)
+        got = st.numpy_tree()
+        for (path, leaf) in U.tree_leaves(ref_tree):
+            node = got
+            for k in path:
+                node = node[k]
+            np.testing.assert_allclose(node, leaf.detach().numpy().astype(np.float32), rtol=1e-6)
+    before = [t.clone() for t in st.state_tensors()]
+    r = st.step(loss_of(st.tree()) * float("nan"), 2.0)
+    assert float(r["has_nan"]) == 1.0 and float(st.notfinite_count) == 1.0 and float(st.count) == 4.0
+    for t, b_ in zip(st.state_tensors()[:3], before[:3]):
+        assert torch.equal(t.detach(), b_.detach())
+    # set_params-style reload keeps the moments
+    st.load(tree)
+    np.testing.assert_allclose(st.numpy_tree()["params"]["b"]["kernel"], tree["params"]["b"]["kernel"].astype(np.float32))
+    assert float(st.m.abs().sum()) > 0
