@@ -23,6 +23,8 @@ CASES = {
     "MPELine_n5_obs3": env_np.EnvCfg(env_np.MPE_LINE, n=5, n_obs=3),
     "MPEFormation_n4_obs3": env_np.EnvCfg(env_np.MPE_FORMATION, n=4, n_obs=3),
     "MPEConnectSpread_n3_obs1": env_np.EnvCfg(env_np.MPE_CONNECT_SPREAD, n=3, n_obs=1, area=1.0, obs_radius=0.25),
+    "LidarBicycleTarget_n16_obs3": env_np.EnvCfg(env_np.LIDAR_BICYCLE_TARGET, n=16, n_obs=3),      # BASELINE C4 size
+    "LidarSpread_n64_obs64_synth": env_np.EnvCfg(env_np.LIDAR_SPREAD, n=64, n_obs=64),             # BASELINE C5 size
 }
 
 
@@ -42,7 +44,8 @@ def graph_at(d, t):
     return {k: d[k][:, t] for k in GRAPH_FIELDS}
 
 
-NN_CASES = {"LidarSpread_n3_obs3": 7, "LidarBicycleTarget_n4_obs3": 8, "MPESpread_n8_obs3": 7}
+NN_CASES = {"LidarSpread_n3_obs3": 7, "LidarBicycleTarget_n4_obs3": 8, "MPESpread_n8_obs3": 7,
+            "LidarBicycleTarget_n16_obs3": 8}
 
 
 def load_nn(name):

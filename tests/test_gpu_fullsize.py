@@ -25,7 +25,7 @@ GRAPH_FIELDS = ("nodes", "edges", "states", "receivers", "senders", "node_type",
 SIZES = [("C2", "MPESpread", 8, 3, 4096, 128, 96),
          ("C3", "LidarSpread", 8, 8, 4096, 128, 96),
          ("C4", "LidarBicycleTarget", 16, 3, 2048, 128, 48),
-         ("C5", "LidarSpread", 64, 64, 1024, 16, 6)]
+         ("C5", "LidarSpread", 64, 64, 1024, 128, 6)]
 
 
 def _setup(env_id, n, obs, b, T, seed):

@@ -38,6 +38,10 @@ CASES = {   # name -> (module, class, n_agents, n_obs, n_envs, n_steps)
     "MPELine_n5_obs3": ("dgppo.env.mpe.mpe_line", "MPELine", 5, 3, 4, 5),
     "MPEFormation_n4_obs3": ("dgppo.env.mpe.mpe_formation", "MPEFormation", 4, 3, 4, 5),
     "MPEConnectSpread_n3_obs1": ("dgppo.env.mpe.mpe_connect_spread", "MPEConnectSpread", 3, 1, 4, 5),
+    # BASELINE C4 size (bicycle, n = 16) through the reference's own reset; C5 size (n = 64, obs = 64) from synthetic
+    # states (its reset may not terminate at the default area: SURVEY.md appendix B.5), see run_case(synthetic=True)
+    "LidarBicycleTarget_n16_obs3": ("dgppo.env.lidar_env.lidar_bicycle_target", "LidarBicycleTarget", 16, 3, 2, 3),
+    "LidarSpread_n64_obs64_synth": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 64, 64, 1, 2),
 }
 GRAPH_FIELDS = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
 
@@ -55,7 +59,22 @@ def run_case(name, mod, cls, n, n_obs, n_envs, n_steps):
     obst = {k: [] for k in ("center", "width", "height", "theta", "points")}
     mpe_obs = []
     for e in range(n_envs):
-        g = env.reset(jax.random.PRNGKey(100 + e))
+        if name.endswith("_synth"):
+            # reset's tail on synthetic states (lidar_env/base.py:121-124): uniform positions, no rejection sampling
+            from dgppo.env.lidar_env.base import LidarEnvState
+            A = env.area_size
+            pos = rng.uniform(0, A, (n, 2)).astype(np.float32)
+            vel = rng.uniform(-0.5, 0.5, (n, 2)).astype(np.float32)
+            gp = np.concatenate([rng.uniform(0, A, (n, 2)), np.zeros((n, 2))], axis=1).astype(np.float32)
+            obstacles = env.create_obstacles(jnp.array(rng.uniform(0, A, (n_obs, 2)).astype(np.float32)),
+                                             jnp.array(rng.uniform(0.1, 0.3, n_obs).astype(np.float32)),
+                                             jnp.array(rng.uniform(0.1, 0.3, n_obs).astype(np.float32)),
+                                             jnp.array(rng.uniform(0, 2 * np.pi, n_obs).astype(np.float32)))
+            states = jnp.array(np.concatenate([pos, vel], axis=1))
+            es0 = LidarEnvState(states, jnp.array(gp), obstacles)
+            g = env.get_graph(es0, env.get_lidar_data(states, obstacles))
+        else:
+            g = env.reset(jax.random.PRNGKey(100 + e))
         es = g.env_states
         if hasattr(es, "obstacle") and es.obstacle is not None:
             for k in obst:
@@ -111,7 +130,7 @@ def _flatten(tree, pre=""):
     return out
 
 
-def run_nn():
+def run_nn(only=()):
     """Policy (mode + sample + log_pi), Vh and Vl forward of the reference's own module code
     (nn/gnn.py, nn/mlp.py, nn/rnn.py, algo/module/{policy,value,distribution}.py) under the
     flax / jraph / tfp stand-ins, on graphs taken from the env fixtures."""
@@ -119,7 +138,9 @@ def run_nn():
     from dgppo.algo.module.value import ValueNet
     from dgppo.utils.graph import GraphsTuple
     for name, n, node_dim in (("LidarSpread_n3_obs3", 3, 7), ("LidarBicycleTarget_n4_obs3", 4, 8),
-                              ("MPESpread_n8_obs3", 8, 7)):
+                              ("MPESpread_n8_obs3", 8, 7), ("LidarBicycleTarget_n16_obs3", 16, 8)):
+        if only and name not in only:
+            continue
         d = np.load(os.path.join(OUT, f"ref_{name}.npz"))
         nominal = GraphsTuple(nodes=jnp.zeros((n, node_dim)), edges=jnp.zeros((n, 4)), states=jnp.zeros((n, 4)),
                               n_node=jnp.array(n), n_edge=jnp.array(n), senders=jnp.arange(n),
@@ -177,3 +198,5 @@ if __name__ == "__main__":
     if not only:
         run_gae()
         run_nn()
+    elif any(o.startswith("nn:") for o in only):          # e.g. nn:LidarBicycleTarget_n16_obs3
+        run_nn([o[3:] for o in only if o.startswith("nn:")])
