@@ -1302,12 +1302,12 @@ int launch_gnn_v2(void* stream, const NetP& P, const DgppoNetLayout& L, const fl
   if ((pl.w_off & 3) || (pl.w_fl & 3) || (pl.hw_fl & 3)) return DGPPO_V2_UNSUPPORTED;
 
   cudaStream_t st = (cudaStream_t)stream;
-  // Programmatic dependent launch (weights staged while the predecessor drains): 0 off (default), 1 gnn + head,
-  // 2 gnn only, 3 head only.  Measured on C3: -2.7 % with one rollout stream, but with the default 4 streams
-  // the early-resident blocks hold shared memory the other streams' kernels would have used (+2.9 % with 1,
-  // +-0 with 2), so it stays off unless asked for.
+  // Programmatic dependent launch (weights / TMEM / barriers set up while the predecessor drains): 1 gnn + head
+  // (default), 0 off, 2 gnn only, 3 head only.  Round-2 measurements (captured rollouts, compact record, tcgen05 head;
+  // C3): 512 envs 6.92 -> 5.99 ms per rollout (2: 6.09, 3: 6.82), 4096 envs 28.36 -> 28.16 ms.  (Round 1, FFMA head,
+  // uncaptured, 4 streams: +2.9 %, which is why it used to be opt-in.)
   static const char* pdl_env = getenv("DGPPO_PDL");
-  const int pdl_mode = pdl_env ? atoi(pdl_env) : 0;
+  const int pdl_mode = pdl_env ? atoi(pdl_env) : 1;
   const bool pdl = pdl_mode == 1 || pdl_mode == 2, pdl_h = pdl_mode == 1 || pdl_mode == 3;
   const int n_tiles = (g.n_graphs + g.G - 1) / g.G;
   const int grid1 = n_tiles < 2 * sms ? n_tiles : 2 * sms;
