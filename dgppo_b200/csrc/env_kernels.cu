@@ -5,6 +5,8 @@
 // coalesced float4 / int stores for the graph record.  Arithmetic follows the
 // reference op by op with individually rounded fp32 operations (common.cuh),
 // so masks, indices and states match oracle/env_np.py bit for bit.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dgppo {
@@ -73,6 +75,8 @@ env_step_kernel(EnvConsts k, const float* __restrict__ agent, const float* __res
                 float* __restrict__ next_agent, float* __restrict__ reward,
                 float* __restrict__ cost, int io_pitch, int b, int st_pitch) {
   extern __shared__ float smem[];
+  pdl_launch_dependents();        // the next policy forward (or LiDAR) may be scheduled and stage its weights
+  pdl_wait();                     // launched with programmatic serialization: the actions of the head are visible from here
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * K1_WARPS + warp;
   if (env >= b) return;
@@ -280,6 +284,8 @@ lidar_kernel(EnvConsts k, const float* __restrict__ agent, const float* __restri
              const float* __restrict__ ray_dirs, float* __restrict__ hits, int b, int sd, int predict,
              int a_pitch, int h_pitch) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long item = (long)blockIdx.x * K2_WARPS + warp;
   const int n = k.n, R = k.n_rays, ne = k.n_obs * 4;
@@ -576,8 +582,11 @@ int dgppo::launch_env_step(void* stream, const DgppoEnvCfg* cfg, const float* ag
   const size_t smem = (size_t)K1_WARPS * 5 * k.n * sizeof(float);
   if (smem > 48 * 1024) return DGPPO_ENOTSUP;
   const int grid = (b + K1_WARPS - 1) / K1_WARPS;
-  env_step_kernel<<<grid, K1_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      k, agent, goal, obs_nodes, action, next_agent, reward, cost, io_pitch, b, st_pitch);
+  // programmatic dependent launch after the head (saves the launch latency; measured at 512 envs: 5.99 -> 5.87 ms
+  // per rollout).  K2 is launched normally: as a PDL node its look-ahead branch lost its overlap (6.8 ms).
+  static const char* pe = getenv("DGPPO_PDL_STEP");
+  launch_pdl(!(pe && pe[0] == '0'), env_step_kernel, grid, K1_WARPS * 32, smem, (cudaStream_t)stream,
+             k, agent, goal, obs_nodes, action, next_agent, reward, cost, (int)io_pitch, (int)b, (int)st_pitch);
   return (int)cudaGetLastError();
 }
 
@@ -599,8 +608,8 @@ int dgppo::launch_lidar(void* stream, const DgppoEnvCfg* cfg, const float* agent
   const long items = (long)b * k.n;
   if (items > 0x7fffffffL) return DGPPO_ENOTSUP;
   const int grid = (int)((items + K2_WARPS - 1) / K2_WARPS);
-  lidar_kernel<<<grid, K2_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      k, agent, obstacles, ray_dirs, hits, b, is_bicycle(cfg->kind) ? 5 : 4, predict, a_pitch, h_pitch);
+  launch_pdl(false, lidar_kernel, grid, K2_WARPS * 32, smem, (cudaStream_t)stream,
+             k, agent, obstacles, ray_dirs, hits, (int)b, is_bicycle(cfg->kind) ? 5 : 4, predict, (int)a_pitch, (int)h_pitch);
   return (int)cudaGetLastError();
 }
 
