@@ -411,8 +411,11 @@ def measure(args, w, b, world, rank, local, full):
             "lidar": 4 * (n * 2 + w["obs"] * 13 + n * k_top * 2) if lidar else 0,
             "graph": 4 * (n * sd + n * sd + n_obs_pts * (2 if lidar else 4) + d.n_nodes * d.node_dim + d.n_edges * 4
                           + d.n_nodes * sd + 2 * d.n_edges + d.n_nodes + 2),
-            # nodes + edges + recv + send + rnn in/out + eps + action + log_pi
-            "policy": 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + 2 * d.n_edges + 2 * n * 64 + n * 2 + n * 2 + n),
+            # graph record: nodes + edges + recv + send; compact record: agent + goal + obstacle-node states;
+            # both: + rnn in/out + eps + action + log_pi
+            "policy": 4 * ((n * sd + env.num_goals * sd + n_obs_pts * (2 if lidar else 4)) if args.record == "compact"
+                           else (d.n_nodes * d.node_dim + d.n_edges * 4 + 2 * d.n_edges))
+                      + 4 * (2 * n * 64 + n * 2 + n * 2 + n),
         }
         per_launch_us = {k: kern_ms[k] / T * 1e3 for k in kern_ms}
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # FFMA lanes x 2 flop x max SM clock, TFLOP/s
@@ -434,8 +437,11 @@ def measure(args, w, b, world, rank, local, full):
                          "us_per_launch": upd["ms"]["gae"] * 1e3}
         tr = traffic_record(args.workload, b)
         ach = rk["policy"]["achieved_gbs"]
-        rec_bytes = 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + d.n_nodes * d.state_dim + 2 * d.n_edges
-                         + d.n_nodes + 2 + n * 2 + n * 64 + 1 + n * 2 + n) + 1
+        if args.record == "compact":    # agent state + hits + action + rnn + reward + cost + done + log_pi
+            rec_bytes = 4 * (n * sd + (n * k_top * 2 if lidar else 0) + n * 2 + n * 64 + 1 + n * env.n_cost + n) + 1
+        else:
+            rec_bytes = 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + d.n_nodes * d.state_dim + 2 * d.n_edges
+                             + d.n_nodes + 2 + n * 2 + n * 64 + 1 + n * 2 + n) + 1
         rollout_gbs = rec_bytes * b * world * T / (ms / args.steps * 1e-3) / 1e9
         chunks = algo._n_chunks(b)
         kernels_per_rollout = chunks * (5 if lidar else 4) * T + (2 if lidar else 1)
@@ -464,7 +470,7 @@ def measure(args, w, b, world, rank, local, full):
                                  "roofline_per_kernel has the HBM-bound kernels and the compute view"},
             "roofline_per_kernel": rk,
             "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof),
-            "rollout_streams": chunks,
+            "rollout_streams": chunks, "record": args.record,
             "api_collect_with_reset": ({"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT}
                                        if ms_api is not None else {"unavailable": api_err}),
             "rollout_hbm": {"unique_record_bytes_per_env_step": rec_bytes, "achieved_gbs": rollout_gbs,
