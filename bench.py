@@ -400,6 +400,23 @@ def measure(args, w, b, world, rank, local, full):
                "with torch-autograd gradients, flat gradient all-reduce over the ranks, clip, Adam)"}
         del Vl, Vh, Qh, Ql, ro
 
+    k3_ms = 0.0
+    if args.record == "compact":                # K3 over the whole record in one launch (what a GraphsTuple view costs)
+        torch.cuda.synchronize()
+        record._materialized = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        goal_b = goal_d if goal_d.shape[1] == env.num_goals else goal_d[:, :env.num_goals]
+        record._goal, record._obstacles = goal_b.contiguous(), (None if lidar else obs_d)
+        record.materialize()                    # first call: the caching allocator obtains the output buffers
+        record._materialized = None
+        torch.cuda.synchronize()
+        e0.record()
+        record.materialize()
+        e1.record()
+        torch.cuda.synchronize()
+        k3_ms = e0.elapsed_time(e1)
+        record._materialized = None
+        torch.cuda.empty_cache()
     line = None
     if rank == 0:
         hbm, which = peaks()
@@ -411,15 +428,17 @@ def measure(args, w, b, world, rank, local, full):
             "lidar": 4 * (n * 2 + w["obs"] * 13 + n * k_top * 2) if lidar else 0,
             "graph": 4 * (n * sd + n * sd + n_obs_pts * (2 if lidar else 4) + d.n_nodes * d.node_dim + d.n_edges * 4
                           + d.n_nodes * sd + 2 * d.n_edges + d.n_nodes + 2),
-            # graph record: nodes + edges + recv + send; compact record: agent + goal + obstacle-node states;
-            # both: + rnn in/out + eps + action + log_pi
-            "policy": 4 * ((n * sd + env.num_goals * sd + n_obs_pts * (2 if lidar else 4)) if args.record == "compact"
-                           else (d.n_nodes * d.node_dim + d.n_edges * 4 + 2 * d.n_edges))
-                      + 4 * (2 * n * 64 + n * 2 + n * 2 + n),
+            # the GraphsTuple the policy forward consumes (nodes + edges + recv + send) + rnn in/out +
+            # eps + action + log_pi.  (With the compact record the kernel reads the state instead and never
+            # materialises the graph: `bytes_moved_compact` below, and `traffic` is accordingly smaller.)
+            "policy": 4 * (d.n_nodes * d.node_dim + d.n_edges * 4 + 2 * d.n_edges + 2 * n * 64 + n * 2 + n * 2 + n),
         }
+        policy_compact = 4 * (n * sd + env.num_goals * sd + n_obs_pts * (2 if lidar else 4) + 2 * n * 64 + n * 2 + n * 2 + n)
         per_launch_us = {k: kern_ms[k] / T * 1e3 for k in kern_ms}
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # FFMA lanes x 2 flop x max SM clock, TFLOP/s
         rk = {}
+        if args.record == "compact":        # K3 is not in the loop: time it where it runs, building all b x (T + 1) graphs
+            per_launch_us["graph"] = k3_ms * 1e3 / (T + 1)
         for k in ("step", "graph", "lidar", "policy"):
             if by[k] == 0 or per_launch_us[k] <= 0:
                 continue
@@ -430,6 +449,7 @@ def measure(args, w, b, world, rank, local, full):
             flops = 2 * 0.52e6 * b
             rk["policy"]["fp32_tflops"] = flops / (per_launch_us["policy"] * 1e-6) / 1e12
             rk["policy"]["frac_of_fp32_peak"] = rk["policy"]["fp32_tflops"] / fp32_peak
+            rk["policy"]["bytes_moved_compact"] = policy_compact * b
             rk["policy"]["note"] = ("head GEMMs run as 3xTF32 on tcgen05 (0.79 M tensor MAC per env-step), the GNN "
                                     "layers on the FFMA pipe; counted here as the fp32 work they replace")
         if upd is not None:
@@ -469,7 +489,8 @@ def measure(args, w, b, world, rank, local, full):
                          "note": "issue / tensor bound kernel pair reported against HBM as BASELINE's metric asks; "
                                  "roofline_per_kernel has the HBM-bound kernels and the compute view"},
             "roofline_per_kernel": rk,
-            "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof),
+            "kernel_ms_per_rollout": dict(kern_ms, total_one_stream=ms_prof,
+                                          **({"graph_all_slots_one_launch": k3_ms} if args.record == "compact" else {})),
             "rollout_streams": chunks, "record": args.record,
             "api_collect_with_reset": ({"ms_per_step": ms_api, "value": units / (ms_api * 1e-3), "unit": UNIT}
                                        if ms_api is not None else {"unavailable": api_err}),
