@@ -207,7 +207,14 @@ def run_gpu(args):
                                     "envs_per_gpu": total, "e2e": weak["e2e"]}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: the 8-rank run of this script sat in destroy_process_group() until the
+        # launcher's time limit after the line had been printed (update steps captured in CUDA graphs held the
+        # communicator).  Every rank has finished its work here; exit code 0 for torchrun.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def traffic_record(workload, b):

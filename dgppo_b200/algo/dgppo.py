@@ -494,7 +494,11 @@ class DGPPO(Algorithm):
                         **{k: v.detach() for k, v in pinfo.items()}})
             return out
 
-        use_graph = os.environ.get("DGPPO_UPDATE_GRAPH", "1") != "0"
+        # CUDA-graph replay of the minibatch step: single rank only by default.  With several ranks the step contains
+        # the NCCL all-reduce; capturing it works, but tearing the process group down with such graphs alive hung
+        # (8 ranks, torch 2.11 / NCCL 2.28), so multi-rank runs take the eager step unless DGPPO_UPDATE_GRAPH=2.
+        ug = os.environ.get("DGPPO_UPDATE_GRAPH", "1")
+        use_graph = ug == "2" or (ug == "1" and world == 1)
         info = {}
         for _ in range(self.epoch_ppo):
             idx = np.arange(b)
