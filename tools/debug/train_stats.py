@@ -14,12 +14,22 @@ for a in sys.argv[1:]:
     kw[k] = float(v)
 algo = make_algo("dgppo", env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
                  action_dim=env.action_dim, n_agents=3, batch_size=16384, seed=0, **kw)
+if os.environ.get("VH_INIT") == "safe":      # diagnostic: start from a Vh that calls every state safe (small negative output)
+    t = algo.params["Vh"]
+    t["params"]["Dense_0"]["kernel"] = (t["params"]["Dense_0"]["kernel"] * 0.01).astype(np.float32)
+    t["params"]["Dense_0"]["bias"] = np.full_like(t["params"]["Dense_0"]["bias"], -0.5)
+    algo.set_params("Vh", t)
+    algo.invalidate("Vh")
 if os.environ.get("FORCE_SAFE") == "1":       # plain PPO on the reward: A = -normalised(Ql - Vl)
     orig = algo.cbf_advantage
     def patched(Ql, Vl, Vh, step):
         A, deriv, acbf, safe = orig(Ql, Vl, Vh, step)
         Al = Ql - Vl[:, :-1]
         Al = (Al - Al.mean(1, keepdim=True)) / (Al.std(1, keepdim=True, unbiased=False) + 1e-8)
+        if os.environ.get("A_MODE") == "random":      # pure noise advantages: what does the optimiser do with them?
+            return torch.randn_like(A), deriv, acbf, torch.ones_like(safe)
+        if os.environ.get("A_MODE") == "random_t":    # noise shared by the agents of a step (as the real Al is)
+            return torch.randn_like(A[:, :, :1]).expand_as(A).contiguous(), deriv, acbf, torch.ones_like(safe)
         sgn = float(os.environ.get("A_SIGN", "-1")); return (sgn * Al)[:, :, None].expand_as(A).contiguous(), deriv, acbf, torch.ones_like(safe)
     algo.cbf_advantage = patched
 rng = np.random.default_rng(0)
