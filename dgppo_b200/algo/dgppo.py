@@ -92,6 +92,12 @@ class DGPPO(Algorithm):
         self._packed: Dict[str, tuple] = {}
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed)
+        # The N(0,1) draw behind the one-sample entropy estimate.  TanhTransformedDistribution.entropy seeds it
+        # from Python (distribution.py:40-42: np.random.randint -> jr.PRNGKey), i.e. ONCE, when update_inner is
+        # traced by jax.jit: every graph of every minibatch of every update shares one (n_agents, action_dim)
+        # sample.  Same here: one draw per algorithm instance (checked against the reference's own closure in
+        # tests/test_update_reference.py).
+        self.entropy_eps = torch.randn((n_agents, action_dim), generator=self._gen, device=self.device)
         # the deterministic-rollout keys and the minibatch shuffle are per-rank streams (each rank owns its envs)
         self._np_rng = np.random.default_rng([seed, D.world()[0]])
         self._train: Dict[str, dict] = {}          # per net: torch leaves + Adam state (algo/update.py)
@@ -507,7 +513,7 @@ class DGPPO(Algorithm):
                 ix = torch.as_tensor(mb, dtype=torch.long, device=self.device)
                 g = mb_graphs(crec, arrays, ix)
                 gd = mb_graphs(cdet, det_arrays, ix)
-                eps = torch.randn(rollout.actions[ix].shape, generator=self._gen, device=self.device)
+                eps = self.entropy_eps.expand(len(mb), T, n, self.action_dim)
                 inputs = (g["nodes"], g["edge_feat"], g["sidx"], g["mask"], gd["nodes"], gd["edge_feat"], gd["sidx"],
                           gd["mask"], pp["bT_Ql"][ix], rnn_det[ix], pp["bTah_Qh_det"][ix], rollout.actions[ix],
                           rollout.log_pis[ix], pp["bTa_A"][ix], eps)

@@ -31,6 +31,12 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) {
 __device__ __forceinline__ float nanmin(float a, float b) {
   return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b);
 }
+// NaN-propagating max (jnp.maximum / jnp.max semantics; fmaxf would drop the NaN)
+__device__ __forceinline__ float nanmax(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));       // one FMNMX.NAN
+  return r;
+}
 
 struct GraphDims {
   int sd, nd, n_on, N, E, n_ag, n_ao, n, g;

@@ -43,13 +43,13 @@ __global__ void gae_kernel(const float* __restrict__ hs, const float* __restrict
       const float* hrow = hs_t + ((size_t)t * n + a) * nh;
       hval = hrow[h];
       float hmax = hrow[0];
-      for (int q = 1; q < nh; ++q) hmax = fmaxf(hmax, hrow[q]);
+      for (int q = 1; q < nh; ++q) hmax = nanmax(hmax, hrow[q]);
       disc = one_m_g * hmax;
     }
     float acc = 0.f;
     for (int k = 0; k <= ii; ++k) {
       const float prev = row[k * cols];
-      const float v = is_l ? (lval + gamma * prev) : fmaxf(hval, disc + gamma * prev);
+      const float v = is_l ? (lval + gamma * prev) : nanmax(hval, disc + gamma * prev);
       row[k * cols] = v;
       const float c = (k == 0) ? lam_pow[ii] : lam_pow[ii - k] * one_m_lam;
       acc = fmaf(v, c, acc);
@@ -91,9 +91,9 @@ __global__ void cbf_advantage_kernel(const float* __restrict__ Ql, const float* 
     for (int h = 0; h < nh; ++h) {
       const float v0 = vh[((size_t)t * n + a) * nh + h], v1 = vh[((size_t)(t + 1) * n + a) * nh + h];
       const float d = (v1 - v0) / dt + alpha * v0;
-      const float ac = fmaxf(d + cbf_eps, 0.f);
+      const float ac = nanmax(d + cbf_eps, 0.f);            // jnp.maximum: a NaN residual stays NaN
       safe = safe && (d <= 0.f);
-      amax = fmaxf(amax, ac);
+      amax = nanmax(amax, ac);
       const size_t o = (((size_t)warp * T + t) * n + a) * nh + h;
       if (deriv_out) deriv_out[o] = d;
       if (acbf_out) acbf_out[o] = ac;

@@ -69,6 +69,36 @@ def test_cbf_advantage():
     assert rsf.any() and (~rsf).any()
 
 
+def test_cbf_advantage_and_gae_propagate_nan():
+    """jnp.maximum / jnp.max propagate NaN (dgppo.py:246,255, algo/utils.py:39-41): a NaN Vh must reach
+    Acbf, A and Qh instead of being dropped by the max."""
+    b, T, n, nh = 2, 16, 3, 2
+    hs, l, Vh, Vl = _gae_inputs(b, T, n, nh, 3)
+    Vh[1, 5, 2, 1] = np.nan
+    Ql = np.zeros((b, T), F)
+    A = torch.empty((b, T, n), device="cuda")
+    d = torch.empty((b, T, n, nh), device="cuda")
+    ac = torch.empty_like(d)
+    sf = torch.empty((b, T, n), dtype=torch.uint8, device="cuda")
+    d_Ql, d_Vl, d_Vh, d_hs, d_l = dev(Ql), dev(Vl), dev(Vh), dev(hs), dev(l)
+    assert _lib.lib().dgppo_cbf_advantage(stream(), p(d_Ql), p(d_Vl), p(d_Vh), 0.03, 10.0, 1e-2, 1.0,
+                                          p(A), p(d), p(ac), p(sf), b, T, n, nh) == 0
+    Qh = torch.empty((b, T, n, nh), device="cuda")
+    Qlo = torch.empty((b, T), device="cuda")
+    assert _lib.lib().dgppo_gae(stream(), p(d_hs), p(d_l), p(d_Vh), p(d_Vl), 0.99, 0.95, p(Qh), p(Qlo),
+                                b, T, n, nh) == 0
+    torch.cuda.synchronize()
+    rA, rd, rac, rsf = algo_np.cbf_advantage(Ql, Vl, Vh, 0.03, 10.0, 1e-2, 1.0)
+    assert np.isnan(rA).any()
+    np.testing.assert_array_equal(np.isnan(A.cpu().numpy()), np.isnan(rA))
+    np.testing.assert_array_equal(np.isnan(ac.cpu().numpy()), np.isnan(rac))
+    np.testing.assert_array_equal(sf.cpu().numpy().astype(bool)[np.isnan(rA)], rsf[np.isnan(rA)])
+    rQh, _ = algo_np.compute_dec_ocp_gae(hs[1], l[1], Vh[1], Vl[1], 0.99, 0.95)
+    assert np.isnan(rQh).any()
+    np.testing.assert_array_equal(np.isnan(Qh[1].cpu().numpy()), np.isnan(rQh))
+    assert not np.isnan(Qh[0].cpu().numpy()).any()
+
+
 @pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
 @pytest.mark.parametrize("stochastic", [True, False])
 def test_rollout_per_step_parity(name, stochastic):

@@ -1,6 +1,8 @@
 """Generate tests/golden/ref_*.npz by EXECUTING THE REFERENCE'S OWN SOURCE
 (/root/reference/dgppo/env/..., dgppo/algo/utils.py) under oracle/jaxshim.py
-(a NumPy stand-in for jax; jax itself is not installable in this image).
+(a NumPy stand-in for jax; jax itself is not installable in this image).  Where a real
+jax / flax / jraph / tfp stack is importable the script uses it instead of the stand-ins
+and writes the same files: that run pins the third-party arithmetic the stand-ins restate.
 
     python tools/gen_golden_from_reference.py          # writes tests/golden/
 
@@ -16,10 +18,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import flaxshim, jaxshim  # noqa: E402
-
-flaxshim.install()      # jaxshim + flax.linen / jraph / tfp stand-ins
-import jax  # noqa: E402  (the shim)
+try:                    # a real JAX stack, when one exists: the same script then pins the fixtures against XLA itself
+    import flax  # noqa: F401,E402
+    import jax  # noqa: E402
+    import jraph  # noqa: F401,E402
+    import tensorflow_probability.substrates.jax  # noqa: F401,E402
+    REAL_JAX = True
+except ImportError:     # this image: NumPy stand-ins for jax / flax.linen / jraph / tfp (oracle/jaxshim.py, flaxshim.py)
+    from oracle import flaxshim, jaxshim  # noqa: E402,F401
+    flaxshim.install()
+    import jax  # noqa: E402  (the shim)
+    REAL_JAX = False
 import jax.numpy as jnp  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -171,7 +180,13 @@ def run_nn(only=()):
             key = jax.random.PRNGKey(1000 + 17 * e + t)
             a_s, lp, rnn_out2 = pol.sample_action(p_pol, G, jnp.array(rnn), key)
             assert np.array_equal(np.asarray(rnn_out), np.asarray(rnn_out2))
-            eps = jaxshim._gen(key).standard_normal((n, 2)).astype(np.float32)     # the draw Normal.sample made
+            if REAL_JAX:    # recover the draw behind the sample from the distribution itself: eps = (atanh a - loc) / scale
+                dist, _ = pol.dist.apply(p_pol, G, jnp.array(rnn), n_agents=n)
+                base = dist.distribution.distribution           # Independent -> TanhTransformed -> Normal
+                eps = ((np.arctanh(np.asarray(a_s, np.float64)) - np.asarray(base.loc, np.float64))
+                       / np.asarray(base.scale, np.float64)).astype(np.float32)
+            else:
+                eps = jaxshim._gen(key).standard_normal((n, 2)).astype(np.float32)     # the draw Normal.sample made
             vh, _ = Vh.get_value(p_vh, G, jnp.array(rnn))
             vl_rnn = (rng.standard_normal((1, 1, 1, 64)) * 0.5).astype(np.float32)
             vl, vl_rnn_out = Vl.get_value(p_vl, G, jnp.array(vl_rnn))
