@@ -20,7 +20,8 @@ import torch
 from dgppo_b200.algo import update as U
 from oracle import algo_np, nn_np
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_update_LidarSpread_n3_obs3.npz")
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ("LidarSpread_n3_obs3", "MPEConnectSpread_n3_obs1")      # two cost heads / three (connectivity), LiDAR / MPE graphs
 GROUPS = {       # as in tools/gen_golden_update_from_reference.py
     "policy": ("", "GraphTransformer_0", "GraphTransformer_1", "PolicyGNNHead", "RNN_0", "ScaleHid", "OutputDenseMean",
                "OutputDenseStdTrans"),
@@ -30,8 +31,15 @@ GROUPS = {       # as in tools/gen_golden_update_from_reference.py
 F = np.float32
 
 
-def load():
-    d = np.load(GOLDEN)
+def env_cfg(name):
+    from oracle import env_np
+    from tests.golden_util import CASES as ENV_CASES
+    import dataclasses
+    return dataclasses.replace(ENV_CASES[name], max_step=16) if dataclasses.is_dataclass(ENV_CASES[name]) else ENV_CASES[name]
+
+
+def load(name="LidarSpread_n3_obs3"):
+    d = np.load(os.path.join(GOLDEN_DIR, f"ref_update_{name}.npz"))
     n, n_obs, b, T, rnn_step, step, train_steps = (int(v) for v in d["meta"])
     trees = {}
     for key in d.files:
@@ -56,8 +64,9 @@ def at(g, t):
 
 
 # ------------------------------------------------------------------ pre-pass
-def test_oracle_reproduces_the_reference_prepass():
-    d, trees, hp, (n, n_obs, b, T, rnn_step) = load()
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_the_reference_prepass(name):
+    d, trees, hp, (n, n_obs, b, T, rnn_step) = load(name)
     assert hp["cbf_weight"] == 2.0                        # step 600 of 1000: past the first schedule boundary
     for tag, vh_key in (("ro", "Vh"), ("det", "Vh_det")):
         g = graphs(d, tag, 0, T + 1)
@@ -93,10 +102,10 @@ def test_oracle_reproduces_the_reference_prepass():
 
 
 # -------------------------------------------------------------------- losses
-def _torch_inputs(d, T, n, n_obs, dtype=torch.float64):
-    N = d["ro:nodes"].shape[2]
-    n_ao = (N - 1 - 2 * n) // n
-    gi = U.GraphIndex(n, n, n_ao, N, torch.device("cpu"))
+def _torch_inputs(d, T, n, n_obs, dtype=torch.float64, name="LidarSpread_n3_obs3"):
+    cfg = env_cfg(name)
+    gi = U.GraphIndex(n, cfg.n_ag, cfg.n_ao, cfg.n_nodes, torch.device("cpu"))
+    assert cfg.n_nodes == d["ro:nodes"].shape[2] and cfg.n_edges == d["ro:edges"].shape[2]
 
     def prep(tag):
         a = [torch.tensor(d[f"{tag}:{k}"][:, :T]) for k in ("nodes", "edges", "receivers", "senders")]
@@ -106,9 +115,9 @@ def _torch_inputs(d, T, n, n_obs, dtype=torch.float64):
     return gi, prep("ro"), prep("det")
 
 
-def _losses(d, trees, hp, dims, dtype=torch.float64):
+def _losses(d, trees, hp, dims, dtype=torch.float64, name="LidarSpread_n3_obs3"):
     n, n_obs, b, T, rnn_step = dims
-    gi, g, gd = _torch_inputs(d, T, n, n_obs, dtype)
+    gi, g, gd = _torch_inputs(d, T, n, n_obs, dtype, name)
     tt = lambda a: torch.tensor(np.asarray(a), dtype=dtype)       # noqa: E731
     tp = {k: U.to_torch_tree(trees[k], "cpu", dtype, requires_grad=True) for k in ("policy", "Vl", "Vh")}
     # the entropy draw: ONE (n, action_dim) sample shared by every graph (distribution.py:37-43 under jit)
@@ -122,9 +131,10 @@ def _losses(d, trees, hp, dims, dtype=torch.float64):
     return out, tp
 
 
-def test_losses_equal_the_reference_closures():
-    d, trees, hp, dims = load()
-    out, _ = _losses(d, trees, hp, dims)
+@pytest.mark.parametrize("name", CASES)
+def test_losses_equal_the_reference_closures(name):
+    d, trees, hp, dims = load(name)
+    out, _ = _losses(d, trees, hp, dims, name=name)
     for tag in ("Vl", "Vh", "policy"):
         np.testing.assert_allclose(float(out[tag][0]), float(d[f"loss:{tag}"]), rtol=2e-5, err_msg=tag)
     info = out["policy"][1]
@@ -145,10 +155,11 @@ def _flatten(tree, pre=""):
     return out
 
 
+@pytest.mark.parametrize("name", CASES)
 @pytest.mark.parametrize("tag", ["Vl", "Vh", "policy"])
-def test_autograd_gradients_vs_finite_differences_of_the_reference_closures(tag):
-    d, trees, hp, dims = load()
-    out, tp = _losses(d, trees, hp, dims)
+def test_autograd_gradients_vs_finite_differences_of_the_reference_closures(tag, name):
+    d, trees, hp, dims = load(name)
+    out, tp = _losses(d, trees, hp, dims, name=name)
     loss = out[tag][0]
     flat_t = _flatten(tp[tag])
     grads = dict(zip(flat_t, torch.autograd.grad(loss, list(flat_t.values()), allow_unused=True)))
@@ -171,18 +182,21 @@ def test_autograd_gradients_vs_finite_differences_of_the_reference_closures(tag)
 
 # ------------------------------------------------------------------ rollouts
 def _obstacles(d, tag):
+    if f"{tag}:obs_theta" not in d.files:        # MPE: the obstacles are nodes of the graph
+        return None
     th = d[f"{tag}:obs_theta"].astype(F)
     return dict(center=d[f"{tag}:obs_center"], width=d[f"{tag}:obs_width"], height=d[f"{tag}:obs_height"], theta=th,
                 cos=np.cos(th).astype(F), sin=np.sin(th).astype(F), points=d[f"{tag}:obs_points"])
 
 
-def test_oracle_rollout_replays_the_reference_trajectories():
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_rollout_replays_the_reference_trajectories(name):
     """The reference's `collect` (rollout, trainer/utils.py:22-57: carry stored BEFORE the step) and its
     deterministic `test_rollout` (:60-86: carry stored AFTER the step), both through its own policy, env.step,
     LiDAR and get_graph, against the oracle's scan from the same initial graph: 16 steps, every field."""
     from oracle import env_np
-    d, trees, hp, (n, n_obs, b, T, rnn_step) = load()
-    cfg = env_np.EnvCfg(env_np.LIDAR_SPREAD, n=n, n_obs=n_obs, max_step=T)
+    d, trees, hp, (n, n_obs, b, T, rnn_step) = load(name)
+    cfg = env_cfg(name)
     fields = ("n_node", "n_edge", "nodes", "edges", "states", "receivers", "senders", "node_type")
     # deterministic
     out = algo_np.rollout(cfg, trees["policy"], {k: d[f"det:{k}"][:, 0] for k in fields}, _obstacles(d, "det"), None, T)

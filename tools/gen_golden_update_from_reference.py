@@ -87,12 +87,20 @@ def closure_vars(f):
     return dict(zip(f.__code__.co_freevars, [c.cell_contents for c in f.__closure__]))
 
 
-def run(name="LidarSpread_n3_obs3", n=3, n_obs=3, b=4, T=16, rnn_step=8, step=600, train_steps=1000):
-    from dgppo.env.lidar_env.lidar_spread import LidarSpread
+CASES = {   # name -> (module, class, n_agents, n_obs)
+    "LidarSpread_n3_obs3": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 3, 3),
+    "MPEConnectSpread_n3_obs1": ("dgppo.env.mpe.mpe_connect_spread", "MPEConnectSpread", 3, 1),     # three cost heads
+}
+
+
+def run(name, b=4, T=16, rnn_step=8, step=600, train_steps=1000):
+    import importlib
     import dgppo.algo.dgppo as M
-    params = dict(LidarSpread.PARAMS)
+    mod, cls, n, n_obs = CASES[name]
+    Env = getattr(importlib.import_module(mod), cls)
+    params = dict(Env.PARAMS)
     params["n_obs"] = n_obs
-    env = LidarSpread(num_agents=n, area_size=None, max_step=T, dt=0.03, params=params)
+    env = Env(num_agents=n, area_size=None, max_step=T, dt=0.03, params=params)
     algo = M.DGPPO(env=env, node_dim=env.node_dim, edge_dim=env.edge_dim, state_dim=env.state_dim,
                    action_dim=env.action_dim, n_agents=n, batch_size=b * T, rnn_step=rnn_step, seed=0,
                    train_steps=train_steps)
@@ -133,8 +141,12 @@ def run(name="LidarSpread_n3_obs3", n=3, n_obs=3, b=4, T=16, rnn_step=8, step=60
         save[f"{tag}:rnn_states"] = np.asarray(r.rnn_states).reshape(b, T, n, 64)
         save[f"{tag}:rewards"] = np.asarray(r.rewards)
         save[f"{tag}:costs"] = np.asarray(r.costs)
-        for k in ("center", "width", "height", "theta", "points"):           # each rollout has its own reset
-            save[f"{tag}:obs_{k}"] = np.asarray(getattr(r.graph.env_states.obstacle, k))[:, 0]      # static over t
+        es = r.graph.env_states                                               # each rollout has its own reset
+        if hasattr(es, "obstacle"):
+            for k in ("center", "width", "height", "theta", "points"):
+                save[f"{tag}:obs_{k}"] = np.asarray(getattr(es.obstacle, k))[:, 0]                  # static over t
+        elif es.obs is not None:
+            save[f"{tag}:mpe_obs"] = np.asarray(es.obs)[:, 0]
     save["ro:log_pis"] = np.asarray(ro.log_pis)
     # pre-pass intermediates: the GAE calls' inputs and outputs (dgppo.py:232-237, 268-273), per env
     for tag, calls in (("", gae_calls[:b]), ("_det", gae_calls[b:])):
@@ -184,4 +196,5 @@ def run(name="LidarSpread_n3_obs3", n=3, n_obs=3, b=4, T=16, rnn_step=8, step=60
 
 
 if __name__ == "__main__":
-    run()
+    for case in (sys.argv[1:] or list(CASES)):
+        run(case)
