@@ -24,6 +24,7 @@ before clipping, which reproduces the single-device mean.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -68,11 +69,10 @@ def dense(x, p):
 
 
 def layer_norm(x, p, eps=1e-6):
-    """flax nn.LayerNorm defaults (fast variance, clipped at 0)."""
-    mean = x.mean(-1, keepdim=True)
-    mean2 = (x * x).mean(-1, keepdim=True)
-    var = torch.clamp(mean2 - mean * mean, min=0.0)
-    return (x - mean) * (torch.rsqrt(var + eps) * p["scale"]) + p["bias"]
+    """flax nn.LayerNorm defaults (eps 1e-6, scale + bias over the last axis).  The library's fused kernel pair
+    (forward + backward) instead of ~30 elementwise launches; flax's "fast variance" E[x^2] - E[x]^2 and the
+    two-pass variance used here are the same function (1e-7 apart in fp32)."""
+    return torch.nn.functional.layer_norm(x, x.shape[-1:], p["scale"], p["bias"], eps)
 
 
 def mlp_head(x, p):
@@ -81,12 +81,29 @@ def mlp_head(x, p):
     return x
 
 
-def gru_cell(p_rnn, h, x):
+def gru_weights(p_rnn):
+    """flax GRUCell leaves (ir, iz, in with bias; hr, hz without; hn with bias: rnn.py / SURVEY A.4) -> the
+    (w_ih, w_hh, b_ih, b_hh) of torch.gru_cell, gate order r | z | n.  Built once per loss evaluation."""
     (c,) = list(p_rnn.values())
-    r = torch.sigmoid(dense(x, c["ir"]) + dense(h, c["hr"]))
-    z = torch.sigmoid(dense(x, c["iz"]) + dense(h, c["hz"]))
-    n = torch.tanh(dense(x, c["in"]) + r * dense(h, c["hn"]))
-    return (1.0 - z) * n + z * h
+    w_ih = torch.cat([c["ir"]["kernel"], c["iz"]["kernel"], c["in"]["kernel"]], dim=1).t()
+    w_hh = torch.cat([c["hr"]["kernel"], c["hz"]["kernel"], c["hn"]["kernel"]], dim=1).t()
+    b_ih = torch.cat([c["ir"]["bias"], c["iz"]["bias"], c["in"]["bias"]])
+    zero = torch.zeros_like(c["hn"]["bias"])
+    b_hh = torch.cat([zero, zero, c["hn"]["bias"]])
+    return w_ih, w_hh, b_ih, b_hh
+
+
+def gru_apply(w, h, x):
+    """r = sigmoid(W_ir x + b_ir + W_hr h), z likewise, n = tanh(W_in x + b_in + r (W_hn h + b_hn)),
+    h' = (1 - z) n + z h: flax's GRUCell and torch.gru_cell agree on this form.  Two GEMMs + one fused
+    pointwise kernel each way on CUDA."""
+    shape = h.shape
+    out = torch.gru_cell(x.reshape(-1, x.shape[-1]), h.reshape(-1, shape[-1]), *w)
+    return out.reshape(shape)
+
+
+def gru_cell(p_rnn, h, x):
+    return gru_apply(gru_weights(p_rnn), h, x)
 
 
 class GraphIndex:
@@ -101,8 +118,9 @@ class GraphIndex:
         self.eidx = torch.as_tensor(e.reshape(-1), dtype=torch.long, device=device)     # (n * deg)
 
 
-def graph_transformer(p, x, edge_feat, sidx, mask, gi: GraphIndex, d: int, agents_only: bool):
-    """One GraphTransformer layer + update (nn/gnn.py:78-117) in receiver-major form.
+def graph_transformer_dense(p, x, edge_feat, sidx, mask, nmask, gi: GraphIndex, d: int, agents_only: bool):
+    """One GraphTransformer layer + update (nn/gnn.py:78-117) in receiver-major form, projections as the reference
+    writes them (q, k, v per node).  Kept as the A/B partner of `graph_transformer` (DGPPO_UPDATE_GNN=dense).
     x (B,N,in); edge_feat (B,n,deg,4); sidx (B,n,deg) sender node of each slot; mask (B,n,deg) slot is live."""
     B, N, n, H = x.shape[0], gi.N, gi.n, N_HEADS
     q = dense(x[:, :n], p["Dense_0"]).reshape(B, n, H, d)
@@ -129,13 +147,60 @@ def graph_transformer(p, x, edge_feat, sidx, mask, gi: GraphIndex, d: int, agent
     return torch.relu(torch.cat([upd[:, :n] + agg, upd[:, n:]], dim=1))
 
 
+def graph_transformer(p, x, edge_feat, sidx, mask, nmask, gi: GraphIndex, d: int, agents_only: bool):
+    """The same layer in the kernels' regrouped algebra, which suits the library GEMMs far
+    better than per-node key / value projections: with q_h = x_i Wq_h + bq_h,
+
+        score_h(i, j) = q_h . (Wk_h^T x_j + bk_h) = x_j . (x_i Wqk_h + bqk_h) + (x_i wqb_h + bqb_h)
+        agg(i)        = 1/H sum_h [ (sum_j a_hij x_j) Wv_h + (sum_j a_hij) bv_h + (sum_t a_hit edge_it) We_h ]
+
+    so the layer is one (B n, in) GEMM for the merged query-key rows, two batched GEMMs over whole graphs
+    ((n H, in) x (in, N) scores and (n H, N) x (N, in) weighted sender features), and one (B n, H (in + 5)) x (., d)
+    GEMM for the stacked value | bias | edge block - no per-node k / v tensors, no scatter.  The softmax runs over
+    the sender NODES of a receiver (every live slot of a receiver is a distinct node): `nmask` (B,n,N).
+    Parameters stay the reference's leaves; the merged blocks are formed from them inside the autograd graph."""
+    B, N, n, H = x.shape[0], gi.N, gi.n, N_HEADS
+    IN = x.shape[-1]
+    xa = x[:, :n]
+    Wq, bq = p["Dense_0"]["kernel"].reshape(IN, H, d), p["Dense_0"]["bias"].reshape(H, d)
+    Wk, bk = p["Dense_1"]["kernel"].reshape(IN, H, d), p["Dense_1"]["bias"].reshape(H, d)
+    Wv, bv = p["Dense_2"]["kernel"].reshape(IN, H, d), p["Dense_2"]["bias"].reshape(H, d)
+    We = p["Dense_3"]["kernel"].reshape(-1, H, d)                                        # (4, H, d)
+    W1 = torch.cat([torch.einsum("ahd,chd->ahc", Wq, Wk).reshape(IN, H * IN),            # x_i -> Wk_h^T q_h   (H in)
+                    torch.einsum("ahd,hd->ah", Wq, bk)], dim=1)                          # x_i -> q_h . bk_h   (H)
+    b1 = torch.cat([torch.einsum("hd,chd->hc", bq, Wk).reshape(H * IN), (bq * bk).sum(-1)])
+    t = xa @ W1 + b1                                                                     # (B,n,H in + H)
+    qt, qb = t[..., :H * IN].reshape(B, n * H, IN), t[..., H * IN:]
+    s = (torch.bmm(qt, x.transpose(1, 2)).reshape(B, n, H, N) + qb.unsqueeze(-1)) / math.sqrt(d)
+    m = nmask.unsqueeze(2)                                                               # (B,n,1,N)
+    # segment_softmax per head over the live senders: masked entries get exp(-1e30 - max) = 0 exactly; a receiver
+    # without any live sender would come out uniform, the mask product makes it all-zero (as the reference's
+    # empty segment is)
+    a = torch.softmax(s.masked_fill(~m, -1e30), dim=-1) * m
+    wx = torch.bmm(a.reshape(B, n * H, N), x).reshape(B, n, H, IN)                       # sum_j a x_j
+    # per-slot weights for the edge features (a masked slot points at node 0: zeroed by the slot mask)
+    a_slot = a.gather(3, sidx.unsqueeze(2).expand(B, n, H, gi.deg)) * mask.unsqueeze(2)
+    ae = (a_slot.unsqueeze(-1) * edge_feat.unsqueeze(2)).sum(3)                          # (B,n,H,4)
+    feat = torch.cat([wx, a.sum(-1, keepdim=True), ae], dim=-1).reshape(B * n, H * (IN + 5))
+    Wagg = torch.cat([Wv, bv.unsqueeze(0), We], dim=0).permute(1, 0, 2).reshape(H * (IN + 5), d)
+    agg = (feat @ Wagg).reshape(B, n, d) / H                                             # mean over heads
+    upd = dense(xa if agents_only else x, p["Dense_4"])
+    if agents_only:
+        return torch.relu(upd + agg)
+    return torch.relu(torch.cat([upd[:, :n] + agg, upd[:, n:]], dim=1))
+
+
 def gnn(p, g, gi: GraphIndex, n_layers: int, msg_dim=32, out_dim=64):
     """GraphTransformerGNN (nn/gnn.py:127-142) -> agent embeddings (B,n,64)."""
     x = g["nodes"]
+    # sender-node mask of every receiver: node j is the sender of a live slot of agent i (slots -> distinct nodes)
+    nmask = torch.zeros((x.shape[0], gi.n, gi.N), dtype=x.dtype, device=x.device).scatter_add_(
+        2, g["sidx"], g["mask"].to(x.dtype)) > 0
+    layer = graph_transformer_dense if os.environ.get("DGPPO_UPDATE_GNN") == "dense" else graph_transformer
     for i in range(n_layers):
         last = i == n_layers - 1
-        x = graph_transformer(p[f"GraphTransformer_{i}"], x, g["edge_feat"], g["sidx"], g["mask"], gi,
-                              out_dim if last else msg_dim, agents_only=last)
+        x = layer(p[f"GraphTransformer_{i}"], x, g["edge_feat"], g["sidx"], g["mask"], nmask, gi,
+                  out_dim if last else msg_dim, agents_only=last)
     return x
 
 
@@ -208,18 +273,27 @@ def chunk_graphs(rollout_arrays, idx, T, gi, dtype):
                        recv.reshape(mb * T, -1), send.reshape(mb * T, -1), gi, dtype)
 
 
+def _scan_gru(w, x_all):
+    """GRU over axis 2 of x_all (mb, C, steps, ..., 64) from a zero carry per chunk (informarl.py:365,412):
+    only this recurrence is sequential - the head before it and the output layers after it run once over all
+    slots.  -> carries AFTER each step, same shape as x_all."""
+    h = torch.zeros_like(x_all[:, :, 0])
+    hs = []
+    for t in range(x_all.shape[2]):
+        h = gru_apply(w, h, x_all[:, :, t])
+        hs.append(h)
+    return torch.stack(hs, dim=2)
+
+
 def loss_Vl(params, g, targets, gi, n_layers, rnn_step):
     """update_Vl.get_loss_ (informarl.py:367-374): scan_Vl over chunks of rnn_step slots, zero initial carry.
     g: graphs (mb*T, ...); targets (mb, T)."""
     mb, T = targets.shape
-    emb = gnn(params["params"]["GraphTransformerGNN_0"], g, gi, n_layers).mean(dim=1)       # (mb*T, 64)
-    emb = emb.reshape(mb, T // rnn_step, rnn_step, -1)
-    h = torch.zeros((mb, T // rnn_step, emb.shape[-1]), dtype=emb.dtype, device=emb.device)
-    out = []
-    for t in range(rnn_step):
-        v, h = value_step(params, emb[:, :, t], h)
-        out.append(v[..., 0])
-    Vl = torch.stack(out, dim=2).reshape(mb, T)
+    p = params["params"]
+    emb = gnn(p["GraphTransformerGNN_0"], g, gi, n_layers).mean(dim=1)                      # (mb*T, 64)
+    x = mlp_head(emb, p["ValueGNNHead"]).reshape(mb, T // rnn_step, rnn_step, -1)
+    hs = _scan_gru(gru_weights(p["RNN_0"]), x)
+    Vl = dense(hs, p["Dense_0"]).reshape(mb, T)
     return (0.5 * (Vl - targets) ** 2).mean()
 
 
@@ -236,19 +310,16 @@ def loss_policy(params, g, actions, log_pis_old, adv, eps, gi, n_layers, rnn_ste
     """update_policy.get_loss_ (informarl.py:416-437).  actions (mb,T,n,2), log_pis_old / adv (mb,T,n),
     eps (mb,T,n,2) the N(0,1) draw behind the one-sample entropy estimate."""
     mb, T, n, nu = actions.shape
-    C = T // rnn_step
-    emb = gnn(params["params"]["PolicyNet_0"]["GraphTransformerGNN_0"], g, gi, n_layers)    # (mb*T, n, 64)
-    emb = emb.reshape(mb, C, rnn_step, n, -1)
-    act = actions.reshape(mb, C, rnn_step, n, nu)
-    ep = eps.reshape(mb, C, rnn_step, n, nu)
-    h = torch.zeros((mb, C, n, emb.shape[-1]), dtype=emb.dtype, device=emb.device)
-    lps, ents = [], []
-    for t in range(rnn_step):
-        mean, std, h = policy_step(params, emb[:, :, t], h)
-        lps.append(tanh_normal_log_prob(act[:, :, t], mean, std))
-        ents.append(tanh_normal_entropy(mean, std, ep[:, :, t]))
-    log_pis = torch.stack(lps, dim=2).reshape(mb, T, n)
-    entropy = torch.stack(ents, dim=2).reshape(mb, T, n)
+    p = params["params"]
+    base = p["PolicyNet_0"]
+    emb = gnn(base["GraphTransformerGNN_0"], g, gi, n_layers)                               # (mb*T, n, 64)
+    x = mlp_head(emb, base["PolicyGNNHead"]).reshape(mb, T // rnn_step, rnn_step, n, -1)
+    hs = _scan_gru(gru_weights(base["RNN_0"]), x).reshape(mb, T, n, -1)
+    f = dense(hs, p["ScaleHid"])
+    mean = dense(f, p["OutputDenseMean"])
+    std = torch.nn.functional.softplus(dense(f, p["OutputDenseStdTrans"]) + STD_DEV_INIT_INV) + STD_DEV_MIN
+    log_pis = tanh_normal_log_prob(actions, mean, std)
+    entropy = tanh_normal_entropy(mean, std, eps)
     ratio = torch.exp(log_pis - log_pis_old)
     l1 = -ratio * adv
     l2 = -torch.clamp(ratio, 1.0 - clip_eps, 1.0 + clip_eps) * adv
