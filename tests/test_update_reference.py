@@ -32,10 +32,9 @@ F = np.float32
 
 
 def env_cfg(name):
-    from oracle import env_np
+    """The oracle's static env description of a fixture case (tests/golden_util.py)."""
     from tests.golden_util import CASES as ENV_CASES
-    import dataclasses
-    return dataclasses.replace(ENV_CASES[name], max_step=16) if dataclasses.is_dataclass(ENV_CASES[name]) else ENV_CASES[name]
+    return ENV_CASES[name]
 
 
 def load(name="LidarSpread_n3_obs3"):
