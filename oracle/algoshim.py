@@ -100,7 +100,7 @@ def _vmap_kw(fn, in_axes=0, out_axes=0):
 
 def _independent_entropy(self, **kw):
     e = np.asarray(self.distribution.entropy(**kw))
-    return J._narrow(e.sum(axis=tuple(range(-self.nd, 0)), dtype=F))
+    return J._narrow(e.sum(axis=tuple(range(-self.nd, 0)), dtype=flaxshim.F))
 
 
 @contextlib.contextmanager
@@ -112,6 +112,18 @@ def trace_constants(seed_value: int = 4242):
         yield seed_value
     finally:
         np.random.randint = orig
+
+
+@contextlib.contextmanager
+def x64():
+    """Evaluate under the stand-ins in float64 (what jax_enable_x64 + float64 parameters would do): jaxshim stops
+    narrowing to 32 bits and the flax / tfp stand-ins compute in float64.  Used to take clean finite differences
+    of the reference's loss closures (the closures' captured data stay the float32 arrays of the fp32 run)."""
+    J.X64, flaxshim.F = True, np.float64
+    try:
+        yield
+    finally:
+        J.X64, flaxshim.F = False, np.float32
 
 
 def entropy_eps(seed_value: int, n_agents: int, action_dim: int) -> np.ndarray:
@@ -127,6 +139,7 @@ def install():
         lambda key, data: J.PRNGKey((int(np.asarray(key).ravel()[-1]) * 1000003 + int(np.asarray(data))) % (2 ** 31))
     J._module("flax.training.train_state", TrainState=TrainState)
     J._module("optax", adam=lambda learning_rate, **k: ("adam", learning_rate), apply_if_finite=lambda o, n: o,
-              l2_loss=lambda p, t: J._narrow((F(0.5) * (np.asarray(p, F) - np.asarray(t, F)) ** 2).astype(F)),
+              l2_loss=lambda p, t: J._narrow((0.5 * (np.asarray(p, flaxshim.F) - np.asarray(t, flaxshim.F)) ** 2)
+                                             .astype(flaxshim.F)),
               piecewise_constant_schedule=_piecewise, constant_schedule=lambda v: (lambda step: v))
     flaxshim.Independent.entropy = _independent_entropy

@@ -21,12 +21,13 @@ same convention as oracle/env_np.py.
 from __future__ import annotations
 
 import importlib.machinery
+import os
 import sys
 import types
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+REFERENCE_ROOT = os.environ.get("DGPPO_REFERENCE_ROOT", "/root/reference")
 
 
 # ------------------------------------------------------------------ arrays
@@ -62,7 +63,12 @@ class ShimArray(np.ndarray):
         return _At(self)
 
 
+X64 = False        # True: keep float64 / int64 results (jax_enable_x64); see oracle/algoshim.x64()
+
+
 def _narrow(x):
+    if X64:
+        return x.view(ShimArray) if isinstance(x, np.ndarray) else x
     if isinstance(x, np.ndarray):
         if x.dtype == np.float64:
             x = x.astype(np.float32)

@@ -6,10 +6,11 @@ Checked on the CPU:
   * the oracle (oracle/algo_np.py, oracle/nn_np.py) reproduces every intermediate of the reference's pre-pass:
     Vl scan, Vh with the stored policy carries (and the policy's post-step carry for the final graph), both
     Dec-OCP GAE passes, the CBF advantage merge with the scheduled weight;
-  * algo/update.py's three loss functions equal the values of the reference's `get_loss_` closures, and their
-    torch-autograd gradients agree with central finite differences OF THOSE CLOSURES along seeded directions
-    confined to groups of parameter leaves (fp32 reference arithmetic: the error bar of each comparison is the
-    spread between the two step sizes in the fixture plus a round-off floor).
+  * algo/update.py's three loss functions equal the values of the reference's `get_loss_` closures - to fp32
+    rounding against the fp32 run, to ~1e-9 against the same closures evaluated in float64 (oracle/algoshim.x64) -
+    and their torch-autograd gradients agree with central finite differences OF THOSE CLOSURES along seeded
+    directions confined to groups of parameter leaves (float64 differences: relative 2e-5; the fp32 run's own
+    differences within their error bar).
 """
 import os
 
@@ -21,7 +22,7 @@ from dgppo_b200.algo import update as U
 from oracle import algo_np, nn_np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ("LidarSpread_n3_obs3", "MPEConnectSpread_n3_obs1")      # two cost heads / three (connectivity), LiDAR / MPE graphs
+CASES = ("LidarSpread_n3_obs3", "MPEConnectSpread_n3_obs1", "LidarBicycleTarget_n4_obs3")      # 2 / 3 cost heads, LiDAR / MPE graphs, Spread / Target goals, state_dim 4 / 5
 GROUPS = {       # as in tools/gen_golden_update_from_reference.py
     "policy": ("", "GraphTransformer_0", "GraphTransformer_1", "PolicyGNNHead", "RNN_0", "ScaleHid", "OutputDenseMean",
                "OutputDenseStdTrans"),
@@ -136,6 +137,9 @@ def test_losses_equal_the_reference_closures(name):
     out, _ = _losses(d, trees, hp, dims, name=name)
     for tag in ("Vl", "Vh", "policy"):
         np.testing.assert_allclose(float(out[tag][0]), float(d[f"loss:{tag}"]), rtol=2e-5, err_msg=tag)
+        # ... and the same closure evaluated in float64: the two loss FUNCTIONS agree to ~1e-9 (the entropy draw is
+        # the fixture's fp32-rounded one here, the unrounded one there)
+        np.testing.assert_allclose(float(out[tag][0]), float(d[f"loss64:{tag}"]), rtol=2e-9, err_msg=tag + " (float64)")
     info = out["policy"][1]
     np.testing.assert_allclose(float(info["policy/entropy"]), float(d["aux:policy/entropy"]), rtol=2e-5)
     np.testing.assert_allclose(float(info["policy/total_variation_dist"]),
@@ -172,11 +176,21 @@ def test_autograd_gradients_vs_finite_differences_of_the_reference_closures(tag,
         dd = sum(float((grads[k].double() * torch.tensor(dirs[k] / F(nrm)).double()).sum())
                  for k in flat_np if grads[k] is not None)
         pn = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for k, v in flat_np.items() if group in k))
-        # error bar: step-size spread (truncation) + fp32 round-off of the loss difference over the smaller step
-        bar = 3.0 * abs(fd[gi_, 0] - fd[gi_, 1]) + 4e-7 * abs(float(d[f"loss:{tag}"])) / (0.01 * pn) + 0.02 * abs(dd)
-        assert abs(dd - fd[gi_, 1]) <= bar, (tag, group, dd, fd[gi_].tolist(), bar)
-        worst = max(worst, abs(dd - fd[gi_, 1]) / bar)
-    print(tag, "worst |autograd - fd| / bar:", round(worst, 3))
+        # (1) the closure evaluated in float64 (algoshim.x64), central differences: the reference's directional
+        #     derivative to ~1e-7 relative
+        #     (steps of 1e-6 / 1e-7 / 1e-8 |p|: a ReLU kink inside the largest step happens once in ~50 directions and
+        #     shows as an outlier among the three, so the closest one is compared)
+        fd64 = min((float(v) for v in d[f"fd64:{tag}"][gi_]), key=lambda v: abs(v - dd))
+        assert abs(dd - fd64) <= 2e-5 * abs(fd64) + 1e-9, (tag, group, dd, d[f"fd64:{tag}"][gi_].tolist())
+        worst = max(worst, abs(dd - fd64) / (abs(fd64) + 1e-12))
+        # (2) the fp32 run's own differences (steps of 2 % and 1 % of |p|): consistent within their error bar -
+        #     step-size spread + fp32 round-off of the loss difference; directions whose derivative is below that
+        #     floor, or that cross ReLU / clip kinks within the step, carry no information and are only bounded
+        noise = 4e-7 * abs(float(d[f"loss:{tag}"])) / (0.01 * pn)
+        bar = 3.0 * abs(fd[gi_, 0] - fd[gi_, 1]) + noise + 0.02 * abs(dd)
+        if abs(fd[gi_, 1]) > 5.0 * (noise + abs(fd[gi_, 0] - fd[gi_, 1])):
+            assert abs(dd - fd[gi_, 1]) <= bar, (tag, group, dd, fd[gi_].tolist(), bar)
+    print(tag, name, "worst relative |autograd - fd64|:", f"{worst:.2e}")
 
 
 # ------------------------------------------------------------------ rollouts

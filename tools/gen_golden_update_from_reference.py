@@ -90,6 +90,7 @@ def closure_vars(f):
 CASES = {   # name -> (module, class, n_agents, n_obs)
     "LidarSpread_n3_obs3": ("dgppo.env.lidar_env.lidar_spread", "LidarSpread", 3, 3),
     "MPEConnectSpread_n3_obs1": ("dgppo.env.mpe.mpe_connect_spread", "MPEConnectSpread", 3, 1),     # three cost heads
+    "LidarBicycleTarget_n4_obs3": ("dgppo.env.lidar_env.lidar_bicycle_target", "LidarBicycleTarget", 4, 3),   # state_dim 5, one goal per agent
 }
 
 
@@ -190,6 +191,25 @@ def run(name, b=4, T=16, rnn_step=8, step=600, train_steps=1000):
             fds.append(row)
             print(f"  {tag:6s} group {group or 'all':20s} |p| {pn:8.3f}  fd {row[0]: .6e} {row[1]: .6e}")
         save[f"fd:{tag}"] = np.array(fds, np.float64)                  # (groups, 2)
+        # the same closures evaluated in float64 (algoshim.x64): the loss to ~1e-15 and its directional derivatives
+        # by central differences with steps of 1e-6 / 1e-7 / 1e-8 |p| - no round-off floor, no truncation to speak of
+        with algoshim.x64():
+            flat64 = {k: v.astype(np.float64) for k, v in flat.items()}
+            l64, _ = loss_at(flat64)
+            save[f"loss64:{tag}"] = np.asarray(l64, np.float64)
+            fd64 = []
+            for gi_, group in enumerate(GROUPS[tag]):
+                d = direction(flat, group, seed=1000 + gi_)
+                pn = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for k, v in flat.items() if group in k))
+                row = []
+                for rel in (1e-6, 1e-7, 1e-8):      # three steps: a ReLU / clip kink inside one of them shows as an outlier
+                    h = rel * pn
+                    lp, _ = loss_at({k: v + h * d[k].astype(np.float64) for k, v in flat64.items()})
+                    lm, _ = loss_at({k: v - h * d[k].astype(np.float64) for k, v in flat64.items()})
+                    row.append((float(lp) - float(lm)) / (2.0 * h))
+                fd64.append(row)
+                print(f"  {tag:6s} group {group or 'all':20s} fd64 " + " ".join(f"{v: .9e}" for v in row))
+            save[f"fd64:{tag}"] = np.array(fd64, np.float64)           # (groups, 3)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, f"ref_update_{name}.npz"), **save)
     print("update", name, {k: float(v) for k, v in info.items()})
