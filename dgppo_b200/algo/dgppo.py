@@ -505,29 +505,37 @@ class DGPPO(Algorithm):
         # (8 ranks, torch 2.11 / NCCL 2.28), so multi-rank runs take the eager step unless DGPPO_UPDATE_GRAPH=2.
         ug = os.environ.get("DGPPO_UPDATE_GRAPH", "1")
         use_graph = ug == "2" or (ug == "1" and world == 1)
+        # DGPPO_UPDATE_TF32=1: let the update's GEMMs run as TF32 (XLA's default precision for f32 dots on NVIDIA
+        # GPUs, i.e. what the reference itself trains with); off by default - the update then is fp32 throughout
+        tf32_prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = os.environ.get("DGPPO_UPDATE_TF32", "0") == "1"
         info = {}
-        for _ in range(self.epoch_ppo):
-            idx = np.arange(b)
-            self._np_rng.shuffle(idx)
-            for mb in np.array_split(idx, max(1, b // mb_envs)):
-                ix = torch.as_tensor(mb, dtype=torch.long, device=self.device)
-                g = mb_graphs(crec, arrays, ix)
-                gd = mb_graphs(cdet, det_arrays, ix)
-                eps = self.entropy_eps.expand(len(mb), T, n, self.action_dim)
-                inputs = (g["nodes"], g["edge_feat"], g["sidx"], g["mask"], gd["nodes"], gd["edge_feat"], gd["sidx"],
-                          gd["mask"], pp["bT_Ql"][ix], rnn_det[ix], pp["bTah_Qh_det"][ix], rollout.actions[ix],
-                          rollout.log_pis[ix], pp["bTa_A"][ix], eps)
-                if use_graph:
-                    # the whole minibatch step replayed as one CUDA graph (captured once per minibatch shape)
-                    key = ("update_graph", tuple((tuple(x.shape), x.dtype) for x in inputs))
-                    gs = self._workspaces.get(key)
-                    if gs is None:
-                        states = st_Vl.state_tensors() + st_Vh.state_tensors() + st_pi.state_tensors()
-                        gs = U.GraphedStep(minibatch_step, inputs, states)
-                        self._workspaces[key] = gs
-                    info = dict(gs(*inputs))
-                else:
-                    info = minibatch_step(*inputs)
+        try:
+            for _ in range(self.epoch_ppo):
+                idx = np.arange(b)
+                self._np_rng.shuffle(idx)
+                for mb in np.array_split(idx, max(1, b // mb_envs)):
+                    ix = torch.as_tensor(mb, dtype=torch.long, device=self.device)
+                    g = mb_graphs(crec, arrays, ix)
+                    gd = mb_graphs(cdet, det_arrays, ix)
+                    eps = self.entropy_eps.expand(len(mb), T, n, self.action_dim)
+                    inputs = (g["nodes"], g["edge_feat"], g["sidx"], g["mask"], gd["nodes"], gd["edge_feat"],
+                              gd["sidx"], gd["mask"], pp["bT_Ql"][ix], rnn_det[ix], pp["bTah_Qh_det"][ix],
+                              rollout.actions[ix], rollout.log_pis[ix], pp["bTa_A"][ix], eps)
+                    if use_graph:
+                        # the whole minibatch step replayed as one CUDA graph (captured once per shape and mode)
+                        key = ("update_graph", torch.backends.cuda.matmul.allow_tf32, os.environ.get("DGPPO_UPDATE_GNN"),
+                               os.environ.get("DGPPO_UPDATE_SPLITK"), tuple((tuple(x.shape), x.dtype) for x in inputs))
+                        gs = self._workspaces.get(key)
+                        if gs is None:
+                            states = st_Vl.state_tensors() + st_Vh.state_tensors() + st_pi.state_tensors()
+                            gs = U.GraphedStep(minibatch_step, inputs, states)
+                            self._workspaces[key] = gs
+                        info = dict(gs(*inputs))
+                    else:
+                        info = minibatch_step(*inputs)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         self._sync_params_from_training()
         info["policy/log_pi_min"] = rollout.log_pis.min()
         info["Vl/max_target"], info["Vl/min_target"] = pp["bT_Ql"].max(), pp["bT_Ql"].min()

@@ -63,8 +63,23 @@ def to_numpy_tree(tree):
 
 
 # ------------------------------------------------------------------ layers
+SPLIT_K_ROWS, SPLIT_K = 32768, 64
+
+
+def matmul_rows(x, W):
+    """x @ W for x with very many rows (every slot of a minibatch: 1e5 .. 1e6) and a small W.  The weight gradient
+    of a plain mm is X^T dY with K = rows - one thin GEMM the library runs on a handful of CTAs; written as a batched
+    product over SPLIT_K row blocks against the expanded W, autograd's backward becomes SPLIT_K partial products
+    + a sum (split-K), which fills the machine.  DGPPO_UPDATE_SPLITK=0 keeps the plain product."""
+    rows = x.numel() // x.shape[-1]
+    if rows < SPLIT_K_ROWS or rows % SPLIT_K or os.environ.get("DGPPO_UPDATE_SPLITK", "1") == "0":
+        return x @ W
+    y = torch.bmm(x.reshape(SPLIT_K, rows // SPLIT_K, x.shape[-1]), W.unsqueeze(0).expand(SPLIT_K, *W.shape))
+    return y.reshape(x.shape[:-1] + (W.shape[-1],))
+
+
 def dense(x, p):
-    y = x @ p["kernel"]
+    y = matmul_rows(x, p["kernel"])
     return y + p["bias"] if "bias" in p else y
 
 
@@ -169,7 +184,7 @@ def graph_transformer(p, x, edge_feat, sidx, mask, nmask, gi: GraphIndex, d: int
     W1 = torch.cat([torch.einsum("ahd,chd->ahc", Wq, Wk).reshape(IN, H * IN),            # x_i -> Wk_h^T q_h   (H in)
                     torch.einsum("ahd,hd->ah", Wq, bk)], dim=1)                          # x_i -> q_h . bk_h   (H)
     b1 = torch.cat([torch.einsum("hd,chd->hc", bq, Wk).reshape(H * IN), (bq * bk).sum(-1)])
-    t = xa @ W1 + b1                                                                     # (B,n,H in + H)
+    t = matmul_rows(xa, W1) + b1                                                         # (B,n,H in + H)
     qt, qb = t[..., :H * IN].reshape(B, n * H, IN), t[..., H * IN:]
     s = (torch.bmm(qt, x.transpose(1, 2)).reshape(B, n, H, N) + qb.unsqueeze(-1)) / math.sqrt(d)
     m = nmask.unsqueeze(2)                                                               # (B,n,1,N)
@@ -183,7 +198,7 @@ def graph_transformer(p, x, edge_feat, sidx, mask, nmask, gi: GraphIndex, d: int
     ae = (a_slot.unsqueeze(-1) * edge_feat.unsqueeze(2)).sum(3)                          # (B,n,H,4)
     feat = torch.cat([wx, a.sum(-1, keepdim=True), ae], dim=-1).reshape(B * n, H * (IN + 5))
     Wagg = torch.cat([Wv, bv.unsqueeze(0), We], dim=0).permute(1, 0, 2).reshape(H * (IN + 5), d)
-    agg = (feat @ Wagg).reshape(B, n, d) / H                                             # mean over heads
+    agg = matmul_rows(feat, Wagg).reshape(B, n, d) / H                                   # mean over heads
     upd = dense(xa if agents_only else x, p["Dense_4"])
     if agents_only:
         return torch.relu(upd + agg)

@@ -254,3 +254,23 @@ def test_flat_train_state_matches_leafwise_adam():
     st.load(tree)
     np.testing.assert_allclose(st.numpy_tree()["params"]["b"]["kernel"], tree["params"]["b"]["kernel"].astype(np.float32))
     assert float(st.m.abs().sum()) > 0
+
+
+def test_matmul_rows_split_k_equals_plain_product(monkeypatch):
+    """The split-K form of the many-rows product (batched over row blocks against the expanded weight) and its
+    autograd gradients equal the plain product's."""
+    torch.manual_seed(0)
+    x = torch.randn(512, 128, 7, dtype=torch.float64, requires_grad=True)          # 65,536 rows: above the threshold
+    W = torch.randn(7, 96, dtype=torch.float64, requires_grad=True)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DGPPO_UPDATE_SPLITK", flag)
+        y = U.matmul_rows(x, W)
+        out[flag] = (y.detach(), torch.autograd.grad((y ** 2).sum(), [x, W]))
+    assert out["1"][0].shape == (512, 128, 96)
+    torch.testing.assert_close(out["1"][0], out["0"][0], rtol=1e-13, atol=1e-13)
+    for a, b_ in zip(out["1"][1], out["0"][1]):
+        torch.testing.assert_close(a, b_, rtol=1e-12, atol=1e-9)
+    # few rows, or a row count the blocks do not divide: the plain product
+    small = torch.randn(100, 7, dtype=torch.float64)
+    torch.testing.assert_close(U.matmul_rows(small, W.detach()), small @ W.detach())
