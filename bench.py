@@ -390,16 +390,16 @@ def measure(args, w, b, world, rank, local, full):
         Vh, ms_vh = ev_time(lambda: algo._value_record("Vh", ro, None))
         (Qh, Ql), ms_gae = ev_time(lambda: algo.gae(ro.costs, -ro.rewards, Vh, Vl))
         _, ms_cbf = ev_time(lambda: algo.cbf_advantage(Ql, Vl, Vh, 0))
-        ms_pre = ms_upd = None
+        ms_pre = ms_upd = upd_err = None
         try:
             _, ms_pre = ev_time(lambda: algo.prepass(ro, 0))
             _, ms_upd = ev_time(lambda: algo.update(ro, 0))
-        except RuntimeError:               # the deterministic rollout resets through the sampler (C5: infeasible area)
-            pass
+        except Exception as exc:           # e.g. the deterministic rollout resets through the sampler (C5: infeasible
+            upd_err = f"{type(exc).__name__}: {exc}"[:200]       # area); an auxiliary leg must not cost the metric line
         gae_bytes = 4 * (T * n * 2 + T + (T + 1) * n * 2 + (T + 1) + T * n * 2 + T)
         upd = {"ms": {"scan_Vl": ms_vl, "Vh": ms_vh, "gae": ms_gae, "cbf_advantage": ms_cbf,
                       "prepass_total": ms_pre, "update_total": ms_upd},
-               "graphs": b * (T + 1), "minibatches": max(1, b // max(1, (algo.batch_size // world) // T)),
+               "error": upd_err, "graphs": b * (T + 1), "minibatches": max(1, b // max(1, (algo.batch_size // world) // T)),
                "gae_gbs": gae_bytes * b / (ms_gae * 1e-3) / 1e9,
                "note": "components: one pass over the stochastic record; prepass_total = deterministic rollout (incl. "
                "reset) + Vl scan + Vh and GAE on both records + CBF advantage merge (dgppo.py:136-273); "
